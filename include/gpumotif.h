@@ -1,0 +1,126 @@
+/*
+ * gpumotif.h -- C ABI of libgpumotif.so: rnamotif's per-start-position
+ * descriptor search on one B200 (sm_100a).  Plain pointers and sizes only.
+ *
+ * What it replaces in the reference (dacase/rnamotif v3.1.1):
+ *
+ *   RM_fm_init()      src/find_motif.c:109-162, src/rnamot.h:347
+ *                     -> gm_ctx_create(): takes the compiled descriptor as a
+ *                        flattened gm_plan_t (include/gpumotif_plan.h) instead
+ *                        of reading the front end's globals.
+ *   the record loop   src/rnamot.c:159-185 (fgetseq; RM_find_motif(comp=0);
+ *                     mk_rcmp; RM_find_motif(comp=1))
+ *                     -> gm_db_upload_chars() once per batch of records,
+ *                        then gm_scan().  The reverse complement
+ *                        (mk_rcmp, src/rnamot.c:193-216) is built on the device.
+ *   RM_find_motif()   src/find_motif.c:164-207, src/rnamot.h:348-349, and
+ *                     everything it calls down to the hit sink
+ *                     (src/find_motif.c:245-1824 incl. chk_motif,
+ *                     set_context, chk_sites)
+ *                     -> gm_scan(): every start offset of every record on
+ *                        both strands; candidates come back through
+ *                        gm_hits() in the reference's enumeration order
+ *                        (record, strand 0 then 1, start ascending, DFS order).
+ *   the hit sink's    src/find_motif.c:373-392 (RM_score, print_match) stays on
+ *   tail              the host and is replayed by the caller over gm_hits().
+ *
+ * All functions return 0 on success and a negative value on error; the
+ * message is available from gm_last_error() (thread-local).  The library
+ * never calls exit() and has NO CPU search path: without a usable sm_100a
+ * device every call fails.
+ *
+ * Threading: a gm_ctx is used by one host thread at a time; distinct contexts
+ * (e.g. one per GPU / per process) are independent.
+ */
+#ifndef GPUMOTIF_H
+#define GPUMOTIF_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "gpumotif_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gm_ctx gm_ctx;
+
+typedef struct gm_scan_stats {
+	double   kernel_ms;      /* search kernel(s), CUDA events on the ctx stream */
+	double   pack_ms;        /* char -> 4-bit pack kernel of the last upload */
+	double   h2d_ms;         /* host -> device copy of the last upload */
+	double   d2h_ms;         /* hit gather device -> host */
+	double   sort_ms;        /* host sort into enumeration order */
+	uint64_t n_starts;       /* (start, strand) pairs searched */
+	uint64_t n_strand_nt;    /* sum of record lengths x strands in the range */
+	uint64_t n_hits;         /* candidates returned */
+	uint32_t n_launches;     /* kernels launched by the last gm_scan */
+	uint32_t n_retries;      /* re-runs because the hit buffer was too small */
+	uint64_t h2d_bytes, d2h_bytes;
+} gm_scan_stats_t;
+
+const char *gm_last_error(void);
+const char *gm_version(void);
+
+/* number of CUDA devices visible to the process (0 if none) */
+int gm_device_count(void);
+
+/* Validate the plan, select `device`, copy the plan to __constant__ memory.
+ * Replaces RM_fm_init (src/find_motif.c:109). */
+int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device);
+void gm_ctx_destroy(gm_ctx *c);
+
+/* Validate a plan without touching a device (host-side checks only). */
+int gm_plan_check(const gm_plan_t *plan);
+
+/* Upload a batch of records given as the characters FN_fgetseq leaves in its
+ * buffer (src/dbutil.c:42-128: letters only, any case, u or t): record r is
+ * seq[rec_off[r] .. rec_off[r+1]).  The copy goes host -> device as is and is
+ * packed to 4-bit IUPAC codes on the device.  `seq` may be pinned or pageable
+ * host memory.  Replaces the previous batch. */
+int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec);
+
+/* Same, for characters that already live in device memory (a CUDA device
+ * pointer, e.g. torch tensor storage). */
+int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_t *rec_off, int n_rec);
+
+/* Number of nucleotides in the uploaded batch. */
+int64_t gm_db_total_nt(const gm_ctx *c);
+
+/*
+ * Search.  Positions are counted over the concatenation of the uploaded
+ * records; the call owns the starts whose 5' end (in the searched strand)
+ * falls on a nucleotide in [g_begin, g_end) -- pass 0 and gm_db_total_nt()
+ * for everything; disjoint ranges on different contexts / GPUs shard a
+ * database with no exchange.  strands = 1 searches the given strand only
+ * (chk_both_strs = 0), 2 searches both.  Blocks until the candidates are in
+ * host memory, sorted into the reference's enumeration order.
+ * Replaces the two RM_find_motif calls per record (src/rnamot.c:178-184).
+ */
+int gm_scan(gm_ctx *c, int64_t g_begin, int64_t g_end, int strands);
+
+/* Split form for callers that overlap or time the phases: launch enqueues the
+ * kernels on the context's stream and returns; finish waits, gathers and
+ * sorts. */
+int gm_scan_launch(gm_ctx *c, int64_t g_begin, int64_t g_end, int strands);
+int gm_scan_finish(gm_ctx *c);
+
+/* Candidates of the last scan: *n records of *stride bytes each, a
+ * gm_hit_hdr_t followed by n_descr gm_hit_el_t (include/gpumotif_plan.h).
+ * Owned by the context until the next scan. */
+int gm_hits(const gm_ctx *c, const void **hits, size_t *n, size_t *stride);
+
+int gm_stats(const gm_ctx *c, gm_scan_stats_t *out);
+
+/* Tunables (before the first scan): hit-buffer capacity in records (default
+ * 1<<20; grown automatically when a scan overflows), starts per tile. */
+int gm_set_hit_capacity(gm_ctx *c, size_t n_records);
+int gm_set_tile(gm_ctx *c, int starts_per_tile);
+
+/* CUDA stream the context launches on, as a cudaStream_t cast to void*. */
+void *gm_stream(const gm_ctx *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -70,6 +70,7 @@ int gmh_RM_score(int comp, int slen, char sbuf[], IDENT_T **idp)
 int RM_find_motif(int n_searches, SEARCH_T *searches[], SITE_T *sites,
 	char sid[], char sdef[], int comp, int slen, char sbuf[])
 {
+	gmh_open(); /* create the file even when nothing is found */
 	if (comp == 0)
 		gmh_rec++;
 	return gmh_ref_RM_find_motif(n_searches, searches, sites, sid, sdef,

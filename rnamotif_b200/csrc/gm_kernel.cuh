@@ -1,0 +1,491 @@
+// gm_kernel.cuh -- device kernels of libgpumotif (sm_100a).
+//
+//   gm_pack_kernel     chars (what FN_fgetseq leaves, src/dbutil.c:105-111)
+//                      -> 4-bit IUPAC codes, two per byte
+//   gm_search_kernel   persistent CTAs; each takes tiles of consecutive start
+//                      positions from a global counter, stages the packed
+//                      tile + halo into shared memory with one TMA bulk copy
+//                      (cp.async.bulk + mbarrier), expands it to one byte per
+//                      nucleotide for both strands (the reverse complement of
+//                      mk_rcmp, src/rnamot.c:193-216, is built here, so HBM is
+//                      read once for both strands), and runs the search
+//                      machine of gm_search.cuh with lane-level work refill.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gm_search.cuh"
+
+namespace gm {
+
+__constant__ gm_plan_t c_plan;
+__constant__ DevSearch c_ds[GM_MAX_DESCR];
+__constant__ DevParams c_par;
+
+#define GM_REC_CACHE 512
+
+struct ScanArgs {
+	const uint8_t *packed;      // 4-bit codes, nucleotide g in byte g>>1, nibble g&1
+	int64_t total_nt;
+	const int64_t *rec_off;     // n_rec + 1 entries, device
+	int n_rec;
+	int64_t g_begin, g_end;
+	int strands;
+	int64_t n_tiles;
+	unsigned long long *tile_counter;
+	unsigned long long *hit_count;
+	unsigned long long *start_count;
+	uint32_t *hits;             // hit records, stride_words each
+	unsigned long long hit_cap;
+	int stride_words;
+};
+
+// ---------------------------------------------------------------- packing
+
+__device__ __forceinline__ unsigned code_of_char(unsigned ch)
+{
+	ch |= 0x20; // letters only: fold case
+	switch (ch) {
+	case 'a': return 1;  case 'c': return 2;  case 'g': return 4;
+	case 't': case 'u': return 8;
+	case 'r': return 5;  case 'y': return 10; case 'm': return 3;
+	case 'k': return 12; case 's': return 6;  case 'w': return 9;
+	case 'h': return 11; case 'b': return 14; case 'v': return 7;
+	case 'd': return 13; case 'n': return 15;
+	}
+	return 0;
+}
+
+// each thread packs 16 characters (one 128-bit load) into 8 bytes
+__global__ void __launch_bounds__(256) gm_pack_kernel(const uint8_t *__restrict__ chars,
+	uint8_t *__restrict__ packed, int64_t n)
+{
+	int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+	const int64_t step = (int64_t)gridDim.x * blockDim.x * 16;
+	for (; i < n; i += step) {
+		uint32_t w[4];
+		if (i + 16 <= n && ((uintptr_t)(chars + i) & 15) == 0) {
+			const uint4 v = *reinterpret_cast<const uint4 *>(chars + i);
+			w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+		} else {
+			for (int k = 0; k < 4; k++) {
+				uint32_t x = 0;
+				for (int b = 0; b < 4; b++) {
+					int64_t j = i + k * 4 + b;
+					x |= (uint32_t)(j < n ? chars[j] : 0) << (8 * b);
+				}
+				w[k] = x;
+			}
+		}
+		uint32_t out[2] = {0, 0};
+		for (int k = 0; k < 16; k++) {
+			unsigned ch = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
+			unsigned c = ch ? code_of_char(ch) : 0;
+			out[k >> 3] |= c << (4 * (k & 7));
+		}
+		// packed is allocated rounded up to 16 nucleotides
+		*reinterpret_cast<uint2 *>(packed + (i >> 1)) = make_uint2(out[0], out[1]);
+	}
+}
+
+// ------------------------------------------------------------- TMA helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+		: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile(
+		"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+			smem_u32(dst)),
+		"l"(src), "r"(bytes), "r"(smem_u32(bar))
+		: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+
+// -------------------------------------------------------------- the sink
+
+// element type covering window-relative position p, or -1 (fm_window == UNDEF)
+__device__ int wtype(const Lane &L, int p)
+{
+	for (int d = 0; d < L.ND; d++) {
+		uint32_t w = L_EL(L, d);
+		int off = lo16(w), len = hi16(w);
+		if (len > 0 && p >= off && p < off + len)
+			return c_plan.elems[d].type;
+	}
+	return -1;
+}
+__device__ __forceinline__ bool is_ss(const Lane &L, int p, bool undef_is_ss)
+{
+	int t = wtype(L, p);
+	return t == GM_SS || (undef_is_ss && t < 0);
+}
+
+// chk_motif + chk_wchlx/chk_triplex/chk_4plex, src/find_motif.c:1406-1718
+// (chk_phlx never rejects: every path returns TRUE, :1531,1550,1554)
+__device__ bool sink_strict(const Lane &L)
+{
+	for (int d = 0; d < L.ND; d++) {
+		const gm_elem_t &e = c_plan.elems[d];
+		if (!e.strict)
+			continue;
+		if (e.type == GM_H5) {
+			int d3 = e.mates[0];
+			int h5_5 = m_off(L, d), h5_3 = h5_5 + m_len(L, d) - 1;
+			int h3_5 = m_off(L, d3), h3_3 = h3_5 + m_len(L, d3) - 1;
+			unsigned dup = c_plan.pairsets[e.pairset].duplex;
+			if (e.strict & GM_5STRICT) {
+				if (L.szero + h5_5 > 0 && L.szero + h3_3 < L.slen - 1) {
+					if (is_ss(L, h5_5 - 1, true) && is_ss(L, h3_3 + 1, true))
+						if (paired(dup, L.sq[h5_5 - 1], L.sq[h3_3 + 1]))
+							return false;
+				}
+			}
+			if (e.strict & GM_3STRICT) {
+				if (is_ss(L, h5_3 + 1, false) && is_ss(L, h3_5 - 1, false))
+					if (paired(dup, L.sq[h5_3 + 1], L.sq[h3_5 - 1]))
+						return false;
+			}
+		} else if (e.type == GM_T1) {
+			int d1 = e.mates[0], d2 = e.mates[1];
+			int t1_5 = m_off(L, d), t1_3 = t1_5 + m_len(L, d) - 1;
+			int t2_5 = m_off(L, d1), t2_3 = t2_5 + m_len(L, d1) - 1;
+			int t3_5 = m_off(L, d2), t3_3 = t3_5 + m_len(L, d2) - 1;
+			const gm_pairset_t &ps = c_plan.pairsets[e.pairset];
+			if ((e.strict & GM_5STRICT) && L.szero + t1_5 > 0) {
+				if (is_ss(L, t1_5 - 1, true) && is_ss(L, t2_3 + 1, false) && is_ss(L, t3_5 - 1, false))
+					if (triple(ps, L.sq[t1_5 - 1], L.sq[t2_3 + 1], L.sq[t3_5 - 1]))
+						return false;
+			}
+			if ((e.strict & GM_3STRICT) && L.szero + t3_3 < L.slen - 1) {
+				if (is_ss(L, t1_3 + 1, false) && is_ss(L, t2_5 - 1, false) && is_ss(L, t3_3 + 1, true))
+					if (triple(ps, L.sq[t1_3 + 1], L.sq[t2_5 - 1], L.sq[t3_3 + 1]))
+						return false;
+			}
+		} else if (e.type == GM_Q1) {
+			int d1 = e.mates[0], d2 = e.mates[1], d3 = e.mates[2];
+			int q1_5 = m_off(L, d), q1_3 = q1_5 + m_len(L, d) - 1;
+			int q2_5 = m_off(L, d1), q2_3 = q2_5 + m_len(L, d1) - 1;
+			int q3_5 = m_off(L, d2), q3_3 = q3_5 + m_len(L, d2) - 1;
+			int q4_5 = m_off(L, d3), q4_3 = q4_5 + m_len(L, d3) - 1;
+			const gm_pairset_t &ps = c_plan.pairsets[e.pairset];
+			if (e.strict & GM_5STRICT) {
+				if (L.szero + q1_5 > 0 && L.szero + q4_3 < L.slen - 1) {
+					if (is_ss(L, q1_5 - 1, true) && is_ss(L, q2_3 + 1, false) &&
+					    is_ss(L, q3_5 - 1, false) && is_ss(L, q4_3 + 1, true))
+						if (quad(ps, L.sq[q1_5 - 1], L.sq[q2_3 + 1], L.sq[q3_5 - 1], L.sq[q4_3 + 1]))
+							return false;
+				}
+			}
+			if (e.strict & GM_3STRICT) {
+				// the reference tests st3 twice and never st4 (:1706-1707)
+				if (is_ss(L, q1_3 + 1, false) && is_ss(L, q2_5 - 1, false) && is_ss(L, q3_3 + 1, false))
+					if (quad(ps, L.sq[q1_3 + 1], L.sq[q2_5 - 1], L.sq[q3_3 + 1], L.sq[q4_5 - 1]))
+						return false;
+			}
+		}
+	}
+	return true;
+}
+
+// set_context, src/find_motif.c:1720-1756; results in absolute coordinates
+__device__ bool sink_context(const Lane &L, int ctx[4])
+{
+	ctx[0] = ctx[1] = ctx[2] = ctx[3] = -1;
+	if (c_plan.lctx.present) {
+		int m0 = L.szero + m_off(L, 0);
+		int off = max(m0 - c_plan.lctx.maxlen, 0);
+		int len = m0 - off;
+		ctx[0] = off;
+		ctx[1] = len;
+		if (len < c_plan.lctx.minlen)
+			return false;
+		if (c_plan.lctx.regex >= 0)
+			if (!rx_match(c_plan.regex[c_plan.lctx.regex], L.sq + (off - L.szero), len))
+				return false;
+	}
+	if (c_plan.rctx.present) {
+		int last = L.ND - 1;
+		int roff = L.szero + m_off(L, last) + m_len(L, last);
+		int end = min(roff + c_plan.rctx.maxlen, L.slen);
+		int len = end - roff;
+		ctx[2] = roff;
+		ctx[3] = len;
+		if (len < c_plan.rctx.minlen)
+			return false;
+		if (c_plan.rctx.regex >= 0) {
+			// the reference applies the pattern to the text that starts
+			// at the END of the context (:1745-1751), clipped by the NUL
+			// at slen
+			int avail = max(min(len, L.slen - end), 0);
+			if (!rx_match(c_plan.regex[c_plan.rctx.regex], L.sq + (end - L.szero), avail))
+				return false;
+		}
+	}
+	return true;
+}
+
+// chk_sites / chk_1_site, src/find_motif.c:1758-1808
+__device__ bool sink_sites(const Lane &L)
+{
+	for (int s = 0; s < c_plan.n_sites; s++) {
+		const gm_site_t &si = c_plan.sites[s];
+		int b[4];
+		for (int p = 0; p < si.n_pos; p++) {
+			int d = si.pos[p].elem, off = si.pos[p].offset, at;
+			int mo = m_off(L, d), ml = m_len(L, d);
+			if (si.pos[p].l2r) {
+				if (off > ml)
+					return false;
+				at = mo + off - 1;
+			} else {
+				if (off >= ml)
+					return false;
+				at = mo + ml - off - 1;
+			}
+			b[p] = L.sq[at];
+		}
+		const gm_pairset_t &ps = c_plan.pairsets[si.pairset];
+		int rv = 0;
+		if (si.n_pos == 2)
+			rv = paired(ps.duplex, b[0], b[1]);
+		else if (si.n_pos == 3)
+			rv = triple(ps, b[0], b[1], b[2]);
+		else if (si.n_pos == 4)
+			rv = quad(ps, b[0], b[1], b[2], b[3]);
+		if (!rv)
+			return false;
+	}
+	return true;
+}
+
+// the hit sink up to RM_score, src/find_motif.c:362-372
+__device__ void sink(Lane &L, const ScanArgs &A)
+{
+	int ctx[4];
+	if (c_par.strict_helices && !sink_strict(L))
+		return;
+	if (!sink_context(L, ctx))
+		return;
+	if (c_plan.n_sites > 0 && !sink_sites(L))
+		return;
+	unsigned long long slot = atomicAdd(A.hit_count, 1ull);
+	uint32_t seq = L.seq++;
+	if (slot >= A.hit_cap)
+		return; // counted; the host grows the buffer and re-runs
+	uint32_t *h = A.hits + slot * (unsigned long long)A.stride_words;
+	h[0] = L.rec;
+	h[1] = (uint32_t)L.szero;
+	h[2] = seq;
+	h[3] = (uint32_t)L.comp;
+	h[4] = (uint32_t)ctx[0];
+	h[5] = (uint32_t)ctx[1];
+	h[6] = (uint32_t)ctx[2];
+	h[7] = (uint32_t)ctx[3];
+	for (int d = 0; d < L.ND; d++) {
+		uint32_t el = L_EL(L, d), em = L_EM(L, d);
+		h[8 + 2 * d] = (uint32_t)(L.szero + lo16(el));
+		h[9 + 2 * d] = (uint32_t)(hi16(el) & 0xffff) | ((uint32_t)(lo16(em) & 0xff) << 16) |
+			((uint32_t)(hi16(em) & 0xff) << 24);
+	}
+}
+
+// ------------------------------------------------------------ match helpers
+
+__device__ __forceinline__ int chk_seq5(Lane &L, const DevSearch &S, int off, int len)
+{
+	// chk_seq on the head element, src/find_motif.c:1810-1824
+	const gm_regex_t &rx = c_plan.regex[S.rx5];
+	if (S.mm5 > 0) {
+		int n_mm;
+		int ok = rx_match_mm(rx, L.sq + off, len, S.mm5, &n_mm);
+		L_EM(L, S.d) = pk16(lo16(L_EM(L, S.d)), n_mm);
+		return ok;
+	}
+	return rx_match(rx, L.sq + off, len);
+}
+
+// find_minlen / find_maxlen, src/find_motif.c:642-665
+__device__ int pk_minlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
+{
+	int v = 0;
+	for (int d = fd; d <= ld; d++) {
+		int ml = m_len(L, d);
+		v += ml != GM_UNDEF ? ml : lo16(elmm[d]);
+	}
+	return v;
+}
+__device__ int pk_maxlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
+{
+	int v = 0;
+	for (int d = fd; d <= ld; d++) {
+		int ml = m_len(L, d);
+		v += ml != GM_UNDEF ? ml : hi16(elmm[d]);
+	}
+	return v;
+}
+
+// match_phlx, src/find_motif.c:1114-1181
+__device__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int s5, int s3, int s5hi, int s5lo,
+	int *hlen, int *n_mpr)
+{
+	const gm_elem_t &e3 = c_plan.elems[d3];
+	const int b3 = L.sq[s3];
+	for (int s = s5hi; s >= s5lo; s--) {
+		int hl, mpr, l_pr;
+		if (paired(S.duplex, L.sq[s], b3)) {
+			hl = 1; mpr = 0; l_pr = 1;
+		} else if (!(S.ends & GM_5PAIRED)) {
+			hl = 1; mpr = 1; l_pr = 0;
+		} else
+			continue;
+		for (int s1 = s - 1; s1 >= s5; s1--) {
+			if (paired(S.duplex, L.sq[s1], L.sq[s3 - hl]))
+				l_pr = 1;
+			else {
+				l_pr = 0;
+				if (++mpr > S.mplim)
+					return false;
+			}
+			hl++;
+		}
+		if (!l_pr && (S.ends & GM_3PAIRED))
+			return false;
+		if (hl < S.minlen || hl > S.maxlen)
+			return false;
+		if (S.pfrac && mpr > c_plan.lentab[S.lentab + hl])
+			return false;
+		if (S.rx5 >= 0 && !rx_match(c_plan.regex[S.rx5], L.sq + s5, hl))
+			return false;
+		if (e3.regex >= 0 && !rx_match(c_plan.regex[e3.regex], L.sq + s3 - hl + 1, hl))
+			return false;
+		*hlen = hl;
+		*n_mpr = mpr;
+		return true;
+	}
+	return false;
+}
+
+// match_triplex, src/find_motif.c:1183-1232
+__device__ bool match_triplex(Lane &L, const DevSearch &S, int dd1, int s1, int s2, int s3, int tlen, int *n_mpr)
+{
+	const gm_elem_t &e = c_plan.elems[S.d];
+	const gm_elem_t &e1 = c_plan.elems[dd1];
+	const gm_pairset_t &ps = L.ps[e.pairset];
+	const int mplim = c_plan.lentab[e.mptab + tlen];
+	int mpr, l_pr;
+	if (triple(ps, L.sq[s1], L.sq[s2], L.sq[s3 - tlen + 1])) {
+		mpr = 0; l_pr = 1;
+	} else if (!(S.ends & GM_5PAIRED)) {
+		mpr = 1; l_pr = 0;
+	} else
+		return false;
+	for (int t = 1; t < tlen; t++) {
+		if (!triple(ps, L.sq[s1 + t], L.sq[s2 - t], L.sq[s3 - tlen + 1 + t])) {
+			l_pr = 0;
+			if (++mpr > mplim)
+				return false;
+		} else
+			l_pr = 1;
+	}
+	if (!l_pr && (S.ends & GM_3PAIRED))
+		return false;
+	if (e1.regex >= 0 && !rx_match(c_plan.regex[e1.regex], L.sq + s2 - tlen + 1, tlen))
+		return false;
+	*n_mpr = mpr;
+	return true;
+}
+
+// match_4plex, src/find_motif.c:1234-1289: parameters come from q2 (stp1);
+// the loop header resets the mispair count (:1260)
+__device__ bool match_4plex(Lane &L, int dd1, int dd2, int s1, int s2, int s3, int s4, int qlen, int *n_mpr)
+{
+	const gm_elem_t &e1 = c_plan.elems[dd1];
+	const gm_elem_t &e2 = c_plan.elems[dd2];
+	const gm_pairset_t &ps = L.ps[e1.pairset];
+	const int mplim = c_plan.lentab[e1.mptab + qlen];
+	int mpr, l_pr;
+	if (quad(ps, L.sq[s1 + qlen - 1], L.sq[s2], L.sq[s3], L.sq[s4 - qlen + 1])) {
+		l_pr = 1;
+	} else if (!(e1.ends & GM_5PAIRED)) {
+		l_pr = 0;
+	} else
+		return false;
+	mpr = 0;
+	for (int q = 1; q < qlen; q++) {
+		if (!quad(ps, L.sq[s1 + qlen - 1 - q], L.sq[s2 + q], L.sq[s3 - q], L.sq[s4 - qlen + 1 + q])) {
+			l_pr = 0;
+			if (++mpr > mplim)
+				return false;
+		} else
+			l_pr = 1;
+	}
+	if (!l_pr && (e1.ends & GM_3PAIRED))
+		return false;
+	if (e1.regex >= 0 && !rx_match(c_plan.regex[e1.regex], L.sq + s2, qlen))
+		return false;
+	if (e2.regex >= 0 && !rx_match(c_plan.regex[e2.regex], L.sq + s3 - qlen + 1, qlen))
+		return false;
+	*n_mpr = mpr;
+	return true;
+}
+
+// upd_pksearches, src/find_motif.c:667-701
+__device__ void upd_pksearches(Lane &L, int d, int h5, int h3, int hlen)
+{
+	const gm_elem_t &e = c_plan.elems[d];
+	const int d3 = e.mates[0];
+	const gm_elem_t &e3 = c_plan.elems[d3];
+	int id;
+	if (e.scope > 0) {
+		id = c_plan.elems[c_plan.scopes[e.scopes + e.scope - 1]].inner;
+		if (id >= 0) {
+			int si = c_plan.elems[id].searchno;
+			L_ZD(L, si) = pk16(lo16(L_ZD(L, si)), h5 - 1);
+		}
+	}
+	id = e.inner;
+	if (id >= 0) {
+		int si = c_plan.elems[id].searchno;
+		L_ZD(L, si) = pk16(h5 + hlen, hi16(L_ZD(L, si)));
+	}
+	id = c_plan.elems[c_plan.scopes[e3.scopes + e3.scope - 1]].inner;
+	if (id >= 0) {
+		int si = c_plan.elems[id].searchno;
+		L_ZD(L, si) = pk16(lo16(L_ZD(L, si)), h3 - hlen);
+	}
+	if (e3.scope < e3.n_scopes - 1) {
+		id = e3.inner;
+		if (id >= 0) {
+			int si = c_plan.elems[id].searchno;
+			L_ZD(L, si) = pk16(h3 + 1, hi16(L_ZD(L, si)));
+		}
+	}
+}
+
+} // namespace gm

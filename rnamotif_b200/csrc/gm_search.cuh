@@ -1,0 +1,202 @@
+// gm_search.cuh -- the per-start-position descriptor search on the device.
+//
+// One lane runs one (start offset, strand) at a time through an explicit-stack
+// enumeration that visits candidates in exactly the order of the reference's
+// recursion (src/find_motif.c:245-973).  The recursion there always descends
+// from search s to search s+1 (find_ss -> s_forward, find_wchlx/phlx/triplex/
+// 4plex -> the first interior search, find_pknot3 -> searchno+1;
+// gm_plan_check verifies this for every plan), so the stack is an array of
+// per-search frames indexed by s and "return" means s-1.
+//
+// All coordinates are relative to the lane's start offset (szero == 0), which
+// keeps every field in 16 bits; the reference's absolute coordinates differ
+// by the constant szero everywhere except the places noted at the sink.
+//
+// Lanes of a warp are at different depths most of the time; the machine is
+// therefore written as ONE loop whose body is a switch over a small set of
+// phases, so that lanes in the same phase -- whatever their depth -- execute
+// together.  Lane state lives in shared memory as 32-bit words laid out
+// [word][thread] (bank = thread: conflict-free for any mix of depths).
+#pragma once
+
+#include <stdint.h>
+#include "gpumotif_plan.h"
+
+namespace gm {
+
+// kinds of search heads (what find_1_motif dispatches on, src/find_motif.c:289-330)
+enum { K_SS = 0, K_WC = 1, K_PK = 2, K_PH = 3, K_TR = 4, K_QU = 5 };
+
+// hot per-search parameters, derived on the host from gm_plan_t
+struct DevSearch {
+	int kind;
+	int d;          // head element
+	int d3;         // far strand: h3 / p3 / t3 / q4 (mates[last]); -1 for ss
+	int loop;       // find_motif: iterate the span end (src/find_motif.c:255-264)
+	int next_s;     // search of s_next, or -1
+	int minlen, maxlen;
+	int minglen, maxglen;
+	int minilen, maxilen;
+	int ends, pfrac, mplim;
+	unsigned duplex;       // ps_mat[0] as 25 bits
+	int lentab;            // per-length pairfrac table (offset into plan.lentab) or -1
+	int rx5, rx3;          // regex of head / far strand, or -1
+	int mm5;               // mismatch limit of the head (ss only on the device)
+	int last;              // 1 for the final search (hit sink follows)
+	int pad0, pad1, pad2;
+};
+static_assert(sizeof(DevSearch) == 23 * 4, "DevSearch is staged with an odd word stride");
+
+struct DevParams {
+	int n_searches, n_descr;
+	int w_winsize;          // min(rm_dmaxlen, windowsize), src/find_motif.c:179
+	int dminlen;
+	int strict_helices;
+	int halo;               // nucleotides staged on each side of a tile
+	int tile;               // starts per tile
+	int words_per_lane;
+	int has_pk;
+};
+
+#define GM_FW 6  // frame words per search
+
+// phases of the machine
+enum {
+	PH_IDLE = 0, PH_ENTER, PH_SPAN, PH_WX_BEGIN, PH_WX_FIRST, PH_WX_EXT,
+	PH_PK_S5, PH_PK_S3, PH_TR_S, PH_QU_S1, PH_QU_S2, PH_RET
+};
+
+__device__ __forceinline__ uint32_t pk16(int a, int b)
+{
+	return (uint32_t)(a & 0xffff) | ((uint32_t)b << 16);
+}
+__device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffff); }
+__device__ __forceinline__ int hi16(uint32_t w) { return (int)w >> 16; }
+
+// tile byte: low nibble = IUPAC code, high nibble = reference base code 0..4
+__device__ __forceinline__ int bcode_of(int v) { return v >> 4; }
+__device__ __forceinline__ int icode_of(int v) { return v & 15; }
+
+// RM_paired, src/find_motif.c:1291-1302
+__device__ __forceinline__ int paired(unsigned duplex, int v5, int v3)
+{
+	return (duplex >> (bcode_of(v5) * 5 + bcode_of(v3))) & 1u;
+}
+
+struct Lane {
+	// views into shared memory
+	uint32_t *st;            // this thread's column of the state array
+	int nt;                  // threads per block (row stride)
+	const uint8_t *sq;       // sq[rel] = tile byte at window-relative position
+	const DevSearch *ds;     // staged search table
+	const gm_pairset_t *ps;  // staged pairsets
+	int NS, ND;
+	// the start this lane is working on
+	int szero;               // absolute offset in the searched strand
+	int slen;                // record length
+	int comp;
+	uint32_t rec;
+	uint32_t seq;            // candidates emitted so far for this start
+};
+
+// ---- lane state accessors -------------------------------------------------
+#define L_ZD(L, s)     (L).st[(s) * (L).nt]
+#define L_FR(L, s, k)  (L).st[((L).NS + (s) * GM_FW + (k)) * (L).nt]
+#define L_EL(L, d)     (L).st[((L).NS * (1 + GM_FW) + (d)) * (L).nt]
+#define L_EM(L, d)     (L).st[((L).NS * (1 + GM_FW) + (L).ND + (d)) * (L).nt]
+
+__device__ __forceinline__ void mark(Lane &L, int d, int off, int len)
+{
+	L_EL(L, d) = pk16(off, len);
+}
+__device__ __forceinline__ void unmark(Lane &L, int d)
+{
+	L_EL(L, d) = pk16(GM_UNDEF, GM_UNDEF);
+}
+__device__ __forceinline__ int m_off(const Lane &L, int d) { return lo16(L_EL(L, d)); }
+__device__ __forceinline__ int m_len(const Lane &L, int d) { return hi16(L_EL(L, d)); }
+__device__ __forceinline__ void set_cnt(Lane &L, int d, int mpr, int mm)
+{
+	L_EM(L, d) = pk16(mpr, mm);
+}
+__device__ __forceinline__ void set_mpr(Lane &L, int d, int mpr)
+{
+	L_EM(L, d) = pk16(mpr, hi16(L_EM(L, d)));
+}
+
+// ---- regex: bit-parallel NFA (step/advance, src/regexp.c:389-664) -----------
+// Boolean result only: for the operator subset the plan admits (classes, '.',
+// '*', \{m,n\}, '^', '$') "some backtracking path succeeds" is regular-language
+// membership, which the position automaton decides exactly.
+__device__ int rx_match(const gm_regex_t &rx, const uint8_t *s, int n)
+{
+	const uint64_t skip = rx.skip, star = rx.star;
+	const uint64_t accept = (uint64_t)1 << rx.npos;
+	const int iters = rx.closure_iters;
+	uint64_t a0 = 1;
+	for (int i = 0; i < iters; i++)
+		a0 |= (a0 & skip) << 1;
+	uint64_t a = a0;
+	bool any = (a & accept) != 0;
+	const bool bol = rx.bol != 0, eol = rx.eol != 0;
+	if (!eol && any)
+		return 1;
+	for (int j = 0; j < n; j++) {
+		uint64_t m = a & rx.B[icode_of(s[j])];
+		a = (m << 1) | (m & star);
+		for (int i = 0; i < iters; i++)
+			a |= (a & skip) << 1;
+		if (!bol)
+			a |= a0;
+		if (a & accept) {
+			if (!eol)
+				return 1;
+		}
+		if (a == 0)
+			return 0;
+	}
+	return (a & accept) != 0 ? 1 : 0;
+}
+
+// mm_step/mm_advance, src/mm_regexp.c:353-469 (fixed-length patterns).
+// Returns 1 and the mismatch count of the first (leftmost) placement that
+// stays within l_mm.
+__device__ int rx_match_mm(const gm_regex_t &rx, const uint8_t *s, int n, int l_mm, int *n_mm)
+{
+	const int m = rx.mm_len;
+	const int last = rx.bol ? 0 : n;
+	for (int p1 = 0; p1 <= last; p1++) {
+		int cnt = 0;
+		bool ok = true;
+		for (int k = 0; k < m; k++) {
+			if (p1 + k >= n) { ok = false; break; }
+			uint64_t bit = (uint64_t)1 << k;
+			if (!(rx.dot & bit) && !(rx.B[icode_of(s[p1 + k])] & bit)) {
+				if (++cnt > l_mm) { ok = false; break; }
+			}
+		}
+		if (ok && rx.eol && p1 + m != n)
+			ok = false;
+		if (ok) {
+			*n_mm = cnt;
+			return 1;
+		}
+	}
+	*n_mm = 0;
+	return 0;
+}
+
+// ---- multi-strand pair rules ---------------------------------------------------
+// RM_triple / RM_quad, src/find_motif.c:1304-1331
+__device__ __forceinline__ int triple(const gm_pairset_t &p, int v1, int v2, int v3)
+{
+	int k = (bcode_of(v1) * 5 + bcode_of(v2)) * 5 + bcode_of(v3);
+	return (p.multi[k >> 5] >> (k & 31)) & 1u;
+}
+__device__ __forceinline__ int quad(const gm_pairset_t &p, int v1, int v2, int v3, int v4)
+{
+	int k = ((bcode_of(v1) * 5 + bcode_of(v2)) * 5 + bcode_of(v3)) * 5 + bcode_of(v4);
+	return (p.multi[k >> 5] >> (k & 31)) & 1u;
+}
+
+} // namespace gm

@@ -1,0 +1,700 @@
+// gpumotif.cu -- host side of libgpumotif.so (C ABI in include/gpumotif.h).
+//
+// Owns the device buffers (packed database, record table, hit buffer), derives
+// the hot per-search table from the flattened plan, launches the kernels of
+// gm_machine.cuh on the context's stream and returns the candidates sorted
+// into the reference's enumeration order (src/find_motif.c:184-205: start
+// ascending within strand within record; DFS order within a start).
+//
+// There is no CPU search path in this library.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "gpumotif.h"
+#include "gm_machine.cuh"
+
+using namespace gm;
+
+static thread_local char g_err[512] = "";
+struct gm_ctx;
+static gm_ctx *g_const_owner[64];
+
+static int fail(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+	return -1;
+}
+
+#define CU(call)                                                                        \
+	do {                                                                                \
+		cudaError_t e_ = (call);                                                        \
+		if (e_ != cudaSuccess)                                                          \
+			return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+struct gm_ctx {
+	gm_plan_t plan;
+	DevParams par;
+	DevSearch ds[GM_MAX_DESCR];
+	int device;
+	int n_sm;
+	cudaStream_t stream;
+	cudaEvent_t ev[6];
+	// database
+	uint8_t *d_chars;      // staging for uploaded characters
+	size_t chars_cap;
+	uint8_t *d_packed;
+	size_t packed_cap;
+	int64_t *d_rec_off;
+	size_t rec_cap;
+	std::vector<int64_t> rec_off;
+	int64_t total_nt;
+	// scan
+	unsigned long long *d_counters; // [0] tile, [1] hits, [2] starts
+	uint32_t *d_hits;
+	size_t hit_cap;       // records
+	int stride_words;
+	int threads, blocks;
+	size_t smem_bytes;
+	std::vector<uint32_t> hits;    // sorted, host
+	size_t n_hits;
+	gm_scan_stats_t stats;
+	// pending launch
+	bool pending;
+	int64_t p_begin, p_end;
+	int p_strands;
+};
+
+extern "C" const char *gm_last_error(void) { return g_err; }
+extern "C" const char *gm_version(void) { return "libgpumotif 0.1 (sm_100a)"; }
+
+extern "C" int gm_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+// --------------------------------------------------------------- plan checks
+
+static int kind_of(const gm_plan_t *pl, int d)
+{
+	const gm_elem_t &e = pl->elems[d];
+	switch (e.type) {
+	case GM_SS: return K_SS;
+	case GM_H5: return e.proper ? K_WC : K_PK;
+	case GM_P5: return K_PH;
+	case GM_T1: return K_TR;
+	case GM_Q1: return K_QU;
+	}
+	return -1;
+}
+
+static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
+{
+	if (pl == NULL)
+		return fail("plan is NULL");
+	if (pl->magic != GM_PLAN_MAGIC || pl->version != GM_PLAN_VERSION)
+		return fail("not a gm_plan_t of version %d", GM_PLAN_VERSION);
+	const int NS = pl->n_searches, ND = pl->n_descr;
+	if (ND <= 0 || ND > GM_MAX_DESCR || NS <= 0 || NS > ND)
+		return fail("plan: %d elements / %d searches out of range", ND, NS);
+	if (pl->n_regex < 0 || pl->n_regex > GM_MAX_REGEX || pl->n_pairsets < 0 ||
+	    pl->n_pairsets > GM_MAX_PAIRSET || pl->n_sites < 0 || pl->n_sites > GM_MAX_SITES ||
+	    pl->n_scopes < 0 || pl->n_scopes > GM_MAX_SCOPES || pl->n_lentab < 0 || pl->n_lentab > GM_LENTAB_SIZE)
+		return fail("plan: table sizes out of range");
+	if (pl->dminlen <= 0)
+		return fail("plan: descriptor can match the empty string (dminlen = %d)", pl->dminlen);
+	if (pl->dmaxlen == GM_UNBOUNDED && pl->windowsize > 16000)
+		return fail("plan: unbounded descriptor with windowsize %d > 16000", pl->windowsize);
+	const int W = pl->dmaxlen < pl->windowsize ? pl->dmaxlen : pl->windowsize;
+	if (W > 16000)
+		return fail("plan: window of %d nt exceeds the device limit of 16000", W);
+	int cx = 0;
+	if (pl->lctx.present)
+		cx = std::max(cx, pl->lctx.maxlen);
+	if (pl->rctx.present)
+		cx = std::max(cx, pl->rctx.maxlen);
+	if (cx > 4000)
+		return fail("plan: context of %d nt exceeds the device limit of 4000", cx);
+
+	for (int d = 0; d < ND; d++) {
+		const gm_elem_t &e = pl->elems[d];
+		if (e.type < 0 || e.type >= GM_N_TYPES)
+			return fail("element %d: bad type %d", d, e.type);
+		if (e.maxlen == GM_UNBOUNDED || e.maxlen < 0 || e.minlen < 0 || e.maxlen > 32000)
+			return fail("element %d: length range [%d,%d] not supported", d, e.minlen, e.maxlen);
+		if (e.regex >= pl->n_regex || e.pairset >= pl->n_pairsets)
+			return fail("element %d: table index out of range", d);
+		if (e.type != GM_SS && e.regex >= 0 && e.mismatch > 0)
+			return fail("element %d: mismatch= on a helix strand is not supported on the device", d);
+		if (e.type != GM_SS && e.regex >= 0 && e.minlen == 0)
+			return fail("element %d: seq= on a helix with minlen=0 is undefined in the reference "
+				    "(src/find_motif.c:986-1021 reads an unset candidate)", d);
+		if (e.type != GM_SS && e.maxlen > GM_MAX_HLEN)
+			return fail("element %d: helix maxlen %d > %d", d, e.maxlen, GM_MAX_HLEN);
+		if (e.regex >= 0 && pl->regex[e.regex].npos > GM_RE_MAX_POS)
+			return fail("element %d: regex too long", d);
+	}
+
+	memset(ds, 0, sizeof(DevSearch) * GM_MAX_DESCR);
+	for (int s = 0; s < NS; s++) {
+		const int d = pl->searches[s];
+		if (d < 0 || d >= ND)
+			return fail("search %d: bad element %d", s, d);
+		const gm_elem_t &e = pl->elems[d];
+		DevSearch &S = ds[s];
+		if (e.searchno != s)
+			return fail("search %d: element %d says searchno %d", s, d, e.searchno);
+		S.kind = kind_of(pl, d);
+		if (S.kind < 0)
+			return fail("search %d: element %d of type %d cannot head a search", s, d, e.type);
+		S.d = d;
+		S.d3 = -1;
+		S.loop = e.next >= 0 ? 1 : (e.outer < 0 ? 1 : 0);
+		S.next_s = -1;
+		if (e.next >= 0) {
+			S.next_s = pl->elems[e.next].searchno;
+			if (S.next_s <= s || S.next_s >= NS)
+				return fail("search %d: successor search %d out of order", s, S.next_s);
+		}
+		S.minlen = e.minlen; S.maxlen = e.maxlen;
+		S.minglen = e.minglen; S.maxglen = e.maxglen;
+		S.minilen = e.minilen; S.maxilen = e.maxilen;
+		if (S.loop && (e.maxglen == GM_UNBOUNDED || e.maxglen < 0 || e.minglen < 0))
+			return fail("search %d: unbounded group length", s);
+		S.ends = e.ends; S.pfrac = e.pfrac; S.mplim = e.mplim;
+		S.duplex = e.pairset >= 0 ? pl->pairsets[e.pairset].duplex : 0;
+		S.lentab = e.lentab;
+		S.rx5 = e.regex;
+		S.rx3 = -1;
+		S.mm5 = e.mismatch;
+		S.last = s == NS - 1;
+		if (S.kind != K_SS) {
+			const int need = S.kind == K_TR ? 2 : S.kind == K_QU ? 3 : 1;
+			if (e.n_mates != need)
+				return fail("search %d: element %d has %d mates, expected %d", s, d, e.n_mates, need);
+			for (int k = 0; k < need; k++)
+				if (e.mates[k] <= d || e.mates[k] >= ND)
+					return fail("search %d: bad mate", s);
+			S.d3 = e.mates[need - 1];
+			S.rx3 = pl->elems[S.d3].regex;
+			if (e.pairset < 0)
+				return fail("search %d: helix without a pairset", s);
+			if (S.pfrac && e.lentab < 0)
+				return fail("search %d: pairfrac without a length table", s);
+			if ((S.kind == K_TR && e.mptab < 0) ||
+			    (S.kind == K_QU && pl->elems[e.mates[0]].mptab < 0))
+				return fail("search %d: missing mispair-by-length table", s);
+			if (S.kind == K_TR && pl->pairsets[e.pairset].n_bases != 3)
+				return fail("search %d: triplex needs a 3-base pairset", s);
+			if (S.kind == K_QU && pl->pairsets[pl->elems[e.mates[0]].pairset].n_bases != 4)
+				return fail("search %d: quadruplex needs a 4-base pairset", s);
+		}
+		if (S.last && S.kind != K_SS)
+			return fail("the last search must be a single-strand element");
+		// the recursion of src/find_motif.c always descends to search s+1
+		if (S.kind == K_WC || S.kind == K_PH || S.kind == K_TR || S.kind == K_QU) {
+			if (e.inner < 0 || pl->elems[e.inner].searchno != s + 1)
+				return fail("search %d: helix without an interior (the reference dereferences "
+					    "NULL there, src/find_motif.c:453-454) or interior not searched next", s);
+		}
+		if (S.kind == K_TR) {
+			const gm_elem_t &e1 = pl->elems[e.mates[0]];
+			if (e1.inner < 0 || pl->elems[e1.inner].searchno <= s + 1)
+				return fail("search %d: triplex second interior missing", s);
+		}
+		if (S.kind == K_QU) {
+			for (int k = 0; k < 2; k++) {
+				const gm_elem_t &ek = pl->elems[e.mates[k]];
+				if (ek.inner < 0 || pl->elems[ek.inner].searchno <= s + 1)
+					return fail("search %d: quadruplex interior %d missing", s, k + 2);
+			}
+		}
+		if (S.kind == K_PK) {
+			if (e.minlen == 0)
+				return fail("search %d: pseudoknot helix with minlen=0 is not supported", s);
+			if (e.n_scopes < 4 || e.scopes < 0 || e.scopes + e.n_scopes > pl->n_scopes)
+				return fail("search %d: bad pseudoknot scope list", s);
+			if (s + 1 >= NS)
+				return fail("search %d: pseudoknot helix cannot be the last search", s);
+			const gm_elem_t &e3 = pl->elems[e.mates[0]];
+			if (e3.scope < 1 || e3.scopes < 0 || e3.scopes + e3.n_scopes > pl->n_scopes)
+				return fail("search %d: bad pseudoknot 3' scope", s);
+		}
+		if ((S.kind == K_SS) && !S.last && s + 1 >= NS)
+			return fail("search %d: dangling", s);
+	}
+	for (int s = 0; s < pl->n_sites; s++) {
+		const gm_site_t &si = pl->sites[s];
+		if (si.n_pos < 2 || si.n_pos > 4 || si.pairset < 0 || si.pairset >= pl->n_pairsets)
+			return fail("site %d: malformed", s);
+		for (int p = 0; p < si.n_pos; p++)
+			if (si.pos[p].elem < 0 || si.pos[p].elem >= ND)
+				return fail("site %d: bad element", s);
+	}
+
+	memset(par, 0, sizeof *par);
+	par->n_searches = NS;
+	par->n_descr = ND;
+	par->w_winsize = W;
+	par->dminlen = pl->dminlen;
+	par->strict_helices = pl->strict_helices;
+	par->halo = W + cx + 2;
+	par->words_per_lane = NS * (1 + GM_FW) + 2 * ND;
+	return 0;
+}
+
+extern "C" int gm_plan_check(const gm_plan_t *plan)
+{
+	static thread_local DevSearch ds[GM_MAX_DESCR];
+	DevParams par;
+	return check_plan(plan, ds, &par);
+}
+
+// -------------------------------------------------------------- context
+
+static size_t smem_need(const gm_ctx *c, int threads, int tile)
+{
+	const int Lb = (tile + 2 * c->par.halo + 15) & ~15;
+	size_t n = 64;
+	n += ((Lb >> 1) + 32 + 15) & ~15;
+	n += 2 * (size_t)Lb;
+	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
+	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
+	n += (c->par.n_descr * 4 + 15) & ~15;
+	n += (GM_REC_CACHE + 1) * 8;
+	n += (size_t)c->par.words_per_lane * threads * 4;
+	return n;
+}
+
+static int configure_launch(gm_ctx *c, int tile)
+{
+	// pick the largest block that leaves room for >= 2 CTAs per SM
+	const size_t smem_sm = 227 * 1024;
+	int best_t = 0;
+	for (int t = 256; t >= 32; t >>= 1) {
+		size_t need = smem_need(c, t, tile);
+		if (need <= smem_sm / 2 || (t == 32 && need <= smem_sm)) {
+			best_t = t;
+			break;
+		}
+	}
+	if (best_t == 0) {
+		// shrink the tile
+		return fail("plan needs %zu bytes of shared memory per 32-lane block (limit %zu)",
+			    smem_need(c, 32, tile), smem_sm);
+	}
+	c->threads = best_t;
+	c->par.tile = tile;
+	c->smem_bytes = smem_need(c, best_t, tile);
+	CU(cudaFuncSetAttribute(gm_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+	int per_sm = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gm_search_kernel, c->threads, c->smem_bytes));
+	if (per_sm < 1)
+		return fail("search kernel does not fit on an SM (threads %d, smem %zu)", c->threads, c->smem_bytes);
+	c->blocks = per_sm * c->n_sm;
+	CU(cudaMemcpyToSymbolAsync(c_par, &c->par, sizeof c->par, 0, cudaMemcpyHostToDevice, c->stream));
+	return 0;
+}
+
+extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
+{
+	if (out == NULL)
+		return fail("out is NULL");
+	*out = NULL;
+	gm_ctx *c = new gm_ctx();
+	memset(&c->stats, 0, sizeof c->stats);
+	c->d_chars = c->d_packed = NULL;
+	c->d_rec_off = NULL;
+	c->d_counters = NULL;
+	c->d_hits = NULL;
+	c->chars_cap = c->packed_cap = c->rec_cap = 0;
+	c->total_nt = 0;
+	c->n_hits = 0;
+	c->pending = false;
+	c->stream = NULL;
+	if (check_plan(plan, c->ds, &c->par)) {
+		delete c;
+		return -1;
+	}
+	c->plan = *plan;
+	int n = gm_device_count();
+	if (n <= 0) {
+		delete c;
+		return fail("no CUDA device: libgpumotif has no CPU path");
+	}
+	if (device < 0 || device >= n) {
+		delete c;
+		return fail("device %d out of range (%d visible)", device, n);
+	}
+	c->device = device;
+	for (int i = 0; i < 6; i++)
+		c->ev[i] = NULL;
+	cudaDeviceProp prop;
+	cudaError_t e = cudaSetDevice(device);
+	if (e == cudaSuccess)
+		e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess) {
+		delete c;
+		return fail("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+	}
+	if (prop.major != 10) {
+		delete c;
+		return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+	}
+	c->n_sm = prop.multiProcessorCount;
+	c->stride_words = (int)((sizeof(gm_hit_hdr_t) + plan->n_descr * sizeof(gm_hit_el_t)) / 4);
+	c->hit_cap = (size_t)1 << 20;
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		delete c;
+		return fail("cudaStreamCreate failed");
+	}
+	for (int i = 0; i < 6; i++)
+		cudaEventCreate(&c->ev[i]);
+	if (cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+		gm_ctx_destroy(c);
+		return fail("cudaMalloc(counters) failed");
+	}
+	cudaMemcpyToSymbolAsync(c_plan, &c->plan, sizeof c->plan, 0, cudaMemcpyHostToDevice, c->stream);
+	cudaMemcpyToSymbolAsync(c_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, 0, cudaMemcpyHostToDevice, c->stream);
+	g_const_owner[device < 64 ? device : 63] = device < 64 ? c : NULL;
+	if (configure_launch(c, 2048)) {
+		gm_ctx_destroy(c);
+		return -1;
+	}
+	if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+		gm_ctx_destroy(c);
+		return fail("plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+	}
+	*out = c;
+	return 0;
+}
+
+extern "C" void gm_ctx_destroy(gm_ctx *c)
+{
+	if (c == NULL)
+		return;
+	cudaSetDevice(c->device);
+	if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c)
+		g_const_owner[c->device] = NULL;
+	if (c->stream)
+		cudaStreamSynchronize(c->stream);
+	cudaFree(c->d_chars);
+	cudaFree(c->d_packed);
+	cudaFree(c->d_rec_off);
+	cudaFree(c->d_counters);
+	cudaFree(c->d_hits);
+	for (int i = 0; i < 6; i++)
+		if (c->ev[i])
+			cudaEventDestroy(c->ev[i]);
+	if (c->stream)
+		cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" void *gm_stream(const gm_ctx *c) { return c ? (void *)c->stream : NULL; }
+
+extern "C" int gm_set_hit_capacity(gm_ctx *c, size_t n)
+{
+	if (c == NULL || n == 0)
+		return fail("bad argument");
+	c->hit_cap = n;
+	cudaSetDevice(c->device);
+	cudaFree(c->d_hits);
+	c->d_hits = NULL;
+	return 0;
+}
+
+extern "C" int gm_set_tile(gm_ctx *c, int tile)
+{
+	if (c == NULL || tile < 32 || tile > 32768)
+		return fail("tile must be in [32, 32768]");
+	CU(cudaSetDevice(c->device));
+	return configure_launch(c, tile);
+}
+
+// -------------------------------------------------------------- database
+
+static int ensure(void **p, size_t *cap, size_t need)
+{
+	if (need <= *cap)
+		return 0;
+	cudaFree(*p);
+	*p = NULL;
+	*cap = 0;
+	size_t n = need + need / 8 + 256;
+	CU(cudaMalloc(p, n));
+	*cap = n;
+	return 0;
+}
+
+static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
+{
+	if (n_rec < 0 || rec_off == NULL)
+		return fail("bad record table");
+	if (rec_off[0] != 0)
+		return fail("rec_off[0] must be 0");
+	for (int r = 0; r < n_rec; r++) {
+		if (rec_off[r + 1] < rec_off[r])
+			return fail("rec_off not ascending at %d", r);
+		if (rec_off[r + 1] - rec_off[r] > 0x7ffffff0ll)
+			return fail("record %d longer than 2^31", r);
+	}
+	c->rec_off.assign(rec_off, rec_off + n_rec + 1);
+	c->total_nt = rec_off[n_rec];
+	size_t cap_bytes = c->rec_cap * sizeof(int64_t);
+	if (ensure((void **)&c->d_rec_off, &cap_bytes, (size_t)(n_rec + 1) * sizeof(int64_t)))
+		return -1;
+	c->rec_cap = cap_bytes / sizeof(int64_t);
+	CU(cudaMemcpyAsync(c->d_rec_off, c->rec_off.data(), (size_t)(n_rec + 1) * sizeof(int64_t),
+			   cudaMemcpyHostToDevice, c->stream));
+	return 0;
+}
+
+static int pack_on_device(gm_ctx *c, const uint8_t *d_chars)
+{
+	const int64_t n = c->total_nt;
+	const size_t pbytes = (size_t)(((n + 15) / 16) * 8) + 64;
+	if (ensure((void **)&c->d_packed, &c->packed_cap, pbytes))
+		return -1;
+	CU(cudaEventRecord(c->ev[1], c->stream));
+	if (n > 0) {
+		int64_t groups = (n + 15) / 16;
+		int blocks = (int)std::min<int64_t>((groups + 255) / 256, (int64_t)c->n_sm * 16);
+		gm_pack_kernel<<<blocks, 256, 0, c->stream>>>(d_chars, c->d_packed, n);
+		CU(cudaGetLastError());
+	}
+	CU(cudaEventRecord(c->ev[2], c->stream));
+	return 0;
+}
+
+extern "C" int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	CU(cudaSetDevice(c->device));
+	if (set_records(c, rec_off, n_rec))
+		return -1;
+	const int64_t n = c->total_nt;
+	if (n > 0 && seq == NULL)
+		return fail("seq is NULL");
+	if (ensure((void **)&c->d_chars, &c->chars_cap, (size_t)n + 64))
+		return -1;
+	CU(cudaEventRecord(c->ev[0], c->stream));
+	if (n > 0)
+		CU(cudaMemcpyAsync(c->d_chars, seq, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+	if (pack_on_device(c, c->d_chars))
+		return -1;
+	CU(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+	c->stats.h2d_ms = ms;
+	cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+	c->stats.pack_ms = ms;
+	c->stats.h2d_bytes = (uint64_t)n + (uint64_t)(n_rec + 1) * 8;
+	return 0;
+}
+
+extern "C" int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_t *rec_off, int n_rec)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	CU(cudaSetDevice(c->device));
+	if (set_records(c, rec_off, n_rec))
+		return -1;
+	if (c->total_nt > 0 && d_seq == NULL)
+		return fail("d_seq is NULL");
+	CU(cudaEventRecord(c->ev[0], c->stream));
+	if (pack_on_device(c, (const uint8_t *)d_seq))
+		return -1;
+	CU(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
+	c->stats.pack_ms = ms;
+	c->stats.h2d_ms = 0;
+	c->stats.h2d_bytes = (uint64_t)(n_rec + 1) * 8;
+	return 0;
+}
+
+extern "C" int64_t gm_db_total_nt(const gm_ctx *c) { return c ? c->total_nt : -1; }
+
+// ------------------------------------------------------------------ scan
+
+// __constant__ symbols are per device, not per context: remember whose plan is
+// resident and re-upload when another context of this process scans.
+
+static int bind_plan(gm_ctx *c)
+{
+	if (c->device < 64 && g_const_owner[c->device] == c)
+		return 0;
+	CU(cudaMemcpyToSymbolAsync(c_plan, &c->plan, sizeof c->plan, 0, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyToSymbolAsync(c_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, 0, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyToSymbolAsync(c_par, &c->par, sizeof c->par, 0, cudaMemcpyHostToDevice, c->stream));
+	if (c->device < 64)
+		g_const_owner[c->device] = c;
+	return 0;
+}
+
+static int launch(gm_ctx *c)
+{
+	if (bind_plan(c))
+		return -1;
+	if (c->d_hits == NULL) {
+		CU(cudaMalloc(&c->d_hits, c->hit_cap * (size_t)c->stride_words * 4));
+	}
+	CU(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+	ScanArgs A;
+	A.packed = c->d_packed;
+	A.total_nt = c->total_nt;
+	A.rec_off = c->d_rec_off;
+	A.n_rec = (int)c->rec_off.size() - 1;
+	A.g_begin = c->p_begin;
+	A.g_end = c->p_end;
+	A.strands = c->p_strands;
+	A.n_tiles = (c->p_end - c->p_begin + c->par.tile - 1) / c->par.tile;
+	A.tile_counter = c->d_counters + 0;
+	A.hit_count = c->d_counters + 1;
+	A.start_count = c->d_counters + 2;
+	A.hits = c->d_hits;
+	A.hit_cap = c->hit_cap;
+	A.stride_words = c->stride_words;
+	CU(cudaEventRecord(c->ev[3], c->stream));
+	if (A.n_tiles > 0) {
+		int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
+		gm_search_kernel<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+		CU(cudaGetLastError());
+		c->stats.n_launches++;
+	}
+	CU(cudaEventRecord(c->ev[4], c->stream));
+	return 0;
+}
+
+extern "C" int gm_scan_launch(gm_ctx *c, int64_t g_begin, int64_t g_end, int strands)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	if (c->pending)
+		return fail("a scan is already in flight");
+	if (strands != 1 && strands != 2)
+		return fail("strands must be 1 or 2");
+	if (g_begin < 0 || g_end > c->total_nt || g_begin > g_end)
+		return fail("range [%lld, %lld) outside the database of %lld nt", (long long)g_begin,
+			    (long long)g_end, (long long)c->total_nt);
+	CU(cudaSetDevice(c->device));
+	c->p_begin = g_begin;
+	c->p_end = g_end;
+	c->p_strands = strands;
+	c->stats.n_launches = 0;
+	c->stats.n_retries = 0;
+	c->stats.kernel_ms = 0;
+	if (launch(c))
+		return -1;
+	c->pending = true;
+	return 0;
+}
+
+struct HitKey {
+	uint32_t rec, comp, szero, seq;
+	uint32_t idx;
+};
+
+extern "C" int gm_scan_finish(gm_ctx *c)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	if (!c->pending)
+		return fail("no scan in flight");
+	c->pending = false;
+	CU(cudaSetDevice(c->device));
+	unsigned long long cnt[4];
+	for (;;) {
+		CU(cudaMemcpyAsync(cnt, c->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
+		c->stats.kernel_ms += ms;
+		if (cnt[1] <= c->hit_cap)
+			break;
+		// the hit buffer was too small: nothing is lost, run again with room
+		c->stats.n_retries++;
+		cudaFree(c->d_hits);
+		c->d_hits = NULL;
+		c->hit_cap = (size_t)cnt[1] + (size_t)cnt[1] / 16 + 1024;
+		if (launch(c))
+			return -1;
+	}
+	const size_t n = (size_t)cnt[1];
+	const size_t sw = (size_t)c->stride_words;
+	std::vector<uint32_t> raw(n * sw);
+	auto t0 = std::chrono::steady_clock::now();
+	if (n > 0)
+		CU(cudaMemcpy(raw.data(), c->d_hits, n * sw * 4, cudaMemcpyDeviceToHost));
+	auto t1 = std::chrono::steady_clock::now();
+	// enumeration order: record, strand, start, DFS rank
+	std::vector<HitKey> keys(n);
+	for (size_t i = 0; i < n; i++) {
+		const uint32_t *h = &raw[i * sw];
+		keys[i] = HitKey{h[0], h[3] & 0xff, h[1], h[2], (uint32_t)i};
+	}
+	std::sort(keys.begin(), keys.end(), [](const HitKey &a, const HitKey &b) {
+		if (a.rec != b.rec) return a.rec < b.rec;
+		if (a.comp != b.comp) return a.comp < b.comp;
+		if (a.szero != b.szero) return a.szero < b.szero;
+		return a.seq < b.seq;
+	});
+	c->hits.resize(n * sw);
+	for (size_t i = 0; i < n; i++)
+		memcpy(&c->hits[i * sw], &raw[(size_t)keys[i].idx * sw], sw * 4);
+	auto t2 = std::chrono::steady_clock::now();
+	c->n_hits = n;
+	c->stats.d2h_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+	c->stats.sort_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+	c->stats.d2h_bytes = n * sw * 4 + sizeof cnt;
+	c->stats.n_hits = n;
+	c->stats.n_starts = cnt[2];
+	// strand-nt in range = nucleotides in range x strands
+	c->stats.n_strand_nt = (uint64_t)(c->p_end - c->p_begin) * (uint64_t)c->p_strands;
+	return 0;
+}
+
+extern "C" int gm_scan(gm_ctx *c, int64_t g_begin, int64_t g_end, int strands)
+{
+	if (gm_scan_launch(c, g_begin, g_end, strands))
+		return -1;
+	return gm_scan_finish(c);
+}
+
+extern "C" int gm_hits(const gm_ctx *c, const void **hits, size_t *n, size_t *stride)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	if (hits)
+		*hits = c->hits.data();
+	if (n)
+		*n = c->n_hits;
+	if (stride)
+		*stride = (size_t)c->stride_words * 4;
+	return 0;
+}
+
+extern "C" int gm_stats(const gm_ctx *c, gm_scan_stats_t *out)
+{
+	if (c == NULL || out == NULL)
+		return fail("bad argument");
+	*out = c->stats;
+	return 0;
+}

@@ -1,0 +1,194 @@
+"""ctypes binding of libgpumotif.so (C ABI: include/gpumotif.h) -- the B200
+descriptor search that stands in for rnamotif's RM_fm_init / RM_find_motif
+(reference: src/rnamot.h:347-349, src/find_motif.c:109-207).
+
+There is no CPU path here: if the CUDA library is missing or no sm_100a device
+is visible, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgpumotif.so")
+
+PLAN_BYTES = 32120
+
+
+class ScanStats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("pack_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("sort_ms", C.c_double),
+                ("n_starts", C.c_uint64), ("n_strand_nt", C.c_uint64), ("n_hits", C.c_uint64),
+                ("n_launches", C.c_uint32), ("n_retries", C.c_uint32),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class GpuMotifError(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_ctx_create", "gm_ctx_destroy",
+           "gm_plan_check", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_total_nt",
+           "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
+           "gm_set_hit_capacity", "gm_set_tile", "gm_stream"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GpuMotifError(f"{LIB_PATH} missing: run `make -C rnamotif_b200/csrc` "
+                                "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.gm_last_error.restype = C.c_char_p
+        L.gm_version.restype = C.c_char_p
+        L.gm_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        L.gm_ctx_destroy.argtypes = [C.c_void_p]
+        L.gm_ctx_destroy.restype = None
+        L.gm_plan_check.argtypes = [C.c_char_p]
+        L.gm_db_upload_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.gm_db_set_device_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.gm_db_total_nt.argtypes = [C.c_void_p]
+        L.gm_db_total_nt.restype = C.c_int64
+        L.gm_scan.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int]
+        L.gm_scan_launch.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int]
+        L.gm_scan_finish.argtypes = [C.c_void_p]
+        L.gm_hits.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.gm_stats.argtypes = [C.c_void_p, C.POINTER(ScanStats)]
+        L.gm_set_hit_capacity.argtypes = [C.c_void_p, C.c_size_t]
+        L.gm_set_tile.argtypes = [C.c_void_p, C.c_int]
+        L.gm_stream.argtypes = [C.c_void_p]
+        L.gm_stream.restype = C.c_void_p
+        _lib = L
+    return _lib
+
+
+def _err():
+    return lib().gm_last_error().decode("utf-8", "replace")
+
+
+def plan_field(plan: bytes, idx: int) -> int:
+    """int32 field `idx` of the gm_plan_t header (2 n_descr, 3 n_searches,
+    4 dminlen, 5 dmaxlen, 6 windowsize, 7 strict_helices, 8 chk_both_strs)."""
+    return int(np.frombuffer(plan, dtype=np.int32, count=16)[idx])
+
+
+def hit_dtype(n_descr: int) -> np.dtype:
+    return np.dtype([("rec", "<u4"), ("szero", "<u4"), ("seq", "<u4"), ("comp", "u1"), ("pad", "u1", 3),
+                     ("lctx_off", "<i4"), ("lctx_len", "<i4"), ("rctx_off", "<i4"), ("rctx_len", "<i4"),
+                     ("el", [("off", "<i4"), ("len", "<i2"), ("mpr", "i1"), ("mm", "i1")], n_descr)])
+
+
+def plan_check(plan: bytes) -> str | None:
+    """Host-side validation only (no device needed).  None if the plan is
+    acceptable, else the reason."""
+    if len(plan) != PLAN_BYTES:
+        return f"plan has {len(plan)} bytes, expected {PLAN_BYTES}"
+    return None if lib().gm_plan_check(plan) == 0 else _err()
+
+
+class MotifSearch:
+    """One descriptor on one GPU.  Mirrors the reference seam: construction is
+    RM_fm_init, `find_motif` is the record loop's pair of RM_find_motif calls
+    over a batch of records."""
+
+    def __init__(self, plan: bytes, device: int = 0):
+        if len(plan) != PLAN_BYTES:
+            raise GpuMotifError(f"plan has {len(plan)} bytes, expected {PLAN_BYTES}")
+        self._plan = bytes(plan)
+        self.n_descr = plan_field(plan, 2)
+        self.chk_both_strs = bool(plan_field(plan, 8))
+        self._ctx = C.c_void_p()
+        if lib().gm_ctx_create(C.byref(self._ctx), self._plan, device) != 0:
+            self._ctx = None
+            raise GpuMotifError("gm_ctx_create: " + _err())
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib().gm_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise GpuMotifError(f"{what}: {_err()}")
+
+    def set_tile(self, n: int):
+        self._ck(lib().gm_set_tile(self._ctx, n), "gm_set_tile")
+
+    def set_hit_capacity(self, n: int):
+        self._ck(lib().gm_set_hit_capacity(self._ctx, n), "gm_set_hit_capacity")
+
+    def upload(self, seq, rec_off):
+        """seq: uint8 array of sequence characters (host), rec_off: int64 offsets."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+        self._ck(lib().gm_db_upload_chars(self._ctx, seq.ctypes.data, rec_off.ctypes.data, len(rec_off) - 1),
+                 "gm_db_upload_chars")
+
+    def upload_ptr(self, host_ptr: int, rec_off):
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+        self._ck(lib().gm_db_upload_chars(self._ctx, host_ptr, rec_off.ctypes.data, len(rec_off) - 1),
+                 "gm_db_upload_chars")
+
+    def set_device_chars(self, dev_ptr: int, rec_off):
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+        self._ck(lib().gm_db_set_device_chars(self._ctx, dev_ptr, rec_off.ctypes.data, len(rec_off) - 1),
+                 "gm_db_set_device_chars")
+
+    @property
+    def total_nt(self) -> int:
+        return int(lib().gm_db_total_nt(self._ctx))
+
+    def scan(self, g_begin: int = 0, g_end: int | None = None, strands: int | None = None):
+        if g_end is None:
+            g_end = self.total_nt
+        if strands is None:
+            strands = 2 if self.chk_both_strs else 1
+        self._ck(lib().gm_scan(self._ctx, g_begin, g_end, strands), "gm_scan")
+        return self.hits()
+
+    def scan_launch(self, g_begin: int = 0, g_end: int | None = None, strands: int | None = None):
+        if g_end is None:
+            g_end = self.total_nt
+        if strands is None:
+            strands = 2 if self.chk_both_strs else 1
+        self._ck(lib().gm_scan_launch(self._ctx, g_begin, g_end, strands), "gm_scan_launch")
+
+    def scan_finish(self):
+        self._ck(lib().gm_scan_finish(self._ctx), "gm_scan_finish")
+
+    def hits(self):
+        p, n, st = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._ck(lib().gm_hits(self._ctx, C.byref(p), C.byref(n), C.byref(st)), "gm_hits")
+        dt = hit_dtype(self.n_descr)
+        assert dt.itemsize == st.value
+        if n.value == 0:
+            return np.zeros(0, dtype=dt)
+        buf = (C.c_uint8 * (n.value * st.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt).copy()
+
+    def stats(self) -> ScanStats:
+        s = ScanStats()
+        self._ck(lib().gm_stats(self._ctx, C.byref(s)), "gm_stats")
+        return s
+
+    @property
+    def stream(self) -> int:
+        return int(lib().gm_stream(self._ctx) or 0)
+
+    # reference-named entry: both strands of every record of a batch
+    def find_motif(self, seq, rec_off):
+        self.upload(seq, rec_off)
+        return self.scan()

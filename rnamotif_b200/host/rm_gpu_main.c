@@ -1,0 +1,232 @@
+/*
+ * rm_gpu_main.c -- rnamotif with the search on the GPU.  Same command line,
+ * same stdout.  The front end, the score program, the energy code and the
+ * printer are the reference's (linked from its own objects); the record loop
+ * of src/rnamot.c:125-190 is re-arranged into batches:
+ *
+ *     read a batch of records with the reference's fgetseq
+ *     gm_db_upload_chars + gm_scan          (libgpumotif, include/gpumotif.h)
+ *     for every candidate, in enumeration order: GM_replay_hit (rm_replay.c)
+ *
+ * Environment: GPUMOTIF_DEVICE (default 0), GPUMOTIF_BATCH_NT (default 64 M),
+ * GPUMOTIF_STATS=1 prints per-batch timings to stderr.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "log.h"
+#include "rmdefs.h"
+#include "rnamot.h"
+#include "dbutil.h"
+#include "gpumotif.h"
+
+extern int rm_error;
+extern ARGS_T *rm_args;
+extern FILE *rm_dbfp;
+
+extern int gm_rm_compile(int, char *[]);
+extern int gm_flatten_plan(gm_plan_t *, char *, size_t);
+extern void GM_replay_strand(char[], char[], int, int, char[]);
+extern int GM_replay_hit(const gm_hit_hdr_t *, const gm_hit_el_t *);
+
+typedef struct {
+	char *sid, *sdef;
+	int64_t off;
+	int slen;
+} REC_T;
+
+/* reverse complement as the reference builds it in place (src/rnamot.c:193-216):
+ * a<->t c<->g (u as t), anything else -> n */
+static void revcomp_into(const char *src, int slen, char *dst)
+{
+	static char cmp[256];
+	static int init;
+	int i;
+	if (!init) {
+		init = 1;
+		memset(cmp, 'n', sizeof cmp);
+		cmp['a'] = cmp['A'] = 't';
+		cmp['c'] = cmp['C'] = 'g';
+		cmp['g'] = cmp['G'] = 'c';
+		cmp['t'] = cmp['T'] = 'a';
+		cmp['u'] = cmp['U'] = 'a';
+	}
+	for (i = 0; i < slen; i++)
+		dst[i] = cmp[(unsigned char)src[slen - 1 - i]];
+	dst[slen] = '\0';
+}
+
+static void die_gm(const char *what)
+{
+	fprintf(stderr, "rnamotif_gpu: %s: %s\n", what, gm_last_error());
+	exit(1);
+}
+
+int main(int argc, char *argv[])
+{
+	static gm_plan_t plan;
+	static char sid[SID_SIZE], sdef[SDEF_SIZE];
+	char err[512];
+	gm_ctx *ctx = NULL;
+	IDENT_T *ip;
+	int chk_both_strs, show_progress, ecnt = 0, device = 0, stats = 0, eof = 0;
+	int (*fgetseq)(FILE *, char *, int, char *, int, char *);
+	int64_t batch_nt = 64ll << 20, buf_cap, used;
+	char *buf, *rcbuf = NULL;
+	int rc_cap = 0;
+	REC_T *recs = NULL;
+	int64_t *offs = NULL;
+	int n_recs, cap_recs = 0;
+	const char *ev;
+
+	gm_rm_compile(argc, argv);
+	if (gm_flatten_plan(&plan, err, sizeof err)) {
+		fprintf(stderr, "rnamotif_gpu: descriptor cannot run on the device: %s\n", err);
+		exit(1);
+	}
+	if ((ev = getenv("GPUMOTIF_DEVICE")) != NULL)
+		device = atoi(ev);
+	if ((ev = getenv("GPUMOTIF_BATCH_NT")) != NULL && atoll(ev) > 0)
+		batch_nt = atoll(ev);
+	if ((ev = getenv("GPUMOTIF_STATS")) != NULL)
+		stats = atoi(ev);
+	if (gm_ctx_create(&ctx, &plan, device))
+		die_gm("gm_ctx_create");
+
+	ip = RM_find_id("chk_both_strs");
+	chk_both_strs = ip == NULL ? 1 : ip->i_val.v_value.v_ival;
+	ip = RM_find_id("show_progress");
+	show_progress = ip == NULL ? 0 : ip->i_val.v_value.v_ival;
+
+	if (rm_args->a_dbfmt == NULL || !strcmp(rm_args->a_dbfmt, DT_FASTN))
+		fgetseq = FN_fgetseq;
+	else if (!strcmp(rm_args->a_dbfmt, DT_PIR))
+		fgetseq = PIR_fgetseq;
+	else if (!strcmp(rm_args->a_dbfmt, DT_GENBANK))
+		fgetseq = GB_fgetseq;
+	else {
+		rm_error = TRUE;
+		LOG_ERROR("unknown data format %s.", rm_args->a_dbfmt);
+		exit(1);
+	}
+	rm_dbfp = DB_fnext(rm_dbfp, &rm_args->a_c_dbfname, rm_args->a_n_dbfname, rm_args->a_dbfname);
+	if (rm_dbfp == NULL)
+		exit(1);
+
+	buf_cap = batch_nt + rm_args->a_maxslen + 16;
+	buf = malloc((size_t)buf_cap);
+	if (buf == NULL) {
+		rm_error = TRUE;
+		LOG_ERROR("can't allocate sbuf (s_sbuf=%lld)", (long long)buf_cap);
+		exit(1);
+	}
+	if (RM_fm_init())
+		exit(1);
+
+	RM_setprog(P_BEGIN);
+	RM_score(0, 0, NULL, NULL);
+	RM_setprog(P_MAIN);
+
+	while (!eof) {
+		const void *hits;
+		size_t n_hits, stride, h;
+		int r;
+
+		/* ---- read a batch ---- */
+		n_recs = 0;
+		used = 0;
+		while (used < batch_nt) {
+			int slen = fgetseq(rm_dbfp, sid, SDEF_SIZE, sdef, rm_args->a_maxslen, buf + used);
+			if (slen == EOF) {
+				rm_dbfp = DB_fnext(rm_dbfp, &rm_args->a_c_dbfname, rm_args->a_n_dbfname,
+					rm_args->a_dbfname);
+				if (rm_dbfp == NULL) {
+					eof = 1;
+					break;
+				}
+				continue;
+			}
+			ecnt++;
+			if (show_progress && ecnt % show_progress == 0)
+				fprintf(stderr, "%s: %7d: %s\n", argv[0], ecnt, sid);
+			if (n_recs == cap_recs) {
+				cap_recs = cap_recs ? 2 * cap_recs : 1024;
+				recs = realloc(recs, cap_recs * sizeof *recs);
+				offs = realloc(offs, (cap_recs + 1) * sizeof *offs);
+				if (recs == NULL || offs == NULL) {
+					fprintf(stderr, "rnamotif_gpu: out of memory\n");
+					exit(1);
+				}
+			}
+			recs[n_recs].sid = strdup(sid);
+			recs[n_recs].sdef = strdup(sdef);
+			recs[n_recs].off = used;
+			recs[n_recs].slen = slen;
+			n_recs++;
+			used += slen; /* the NUL fgetseq wrote is overwritten by the next record;
+				       * the replay restores it per record below */
+		}
+		if (n_recs == 0)
+			break;
+		for (r = 0; r < n_recs; r++)
+			offs[r] = recs[r].off;
+		offs[n_recs] = used;
+
+		/* ---- search on the device ---- */
+		if (gm_db_upload_chars(ctx, buf, offs, n_recs))
+			die_gm("gm_db_upload_chars");
+		if (gm_scan(ctx, 0, used, chk_both_strs ? 2 : 1))
+			die_gm("gm_scan");
+		if (gm_hits(ctx, &hits, &n_hits, &stride))
+			die_gm("gm_hits");
+		if (stats) {
+			gm_scan_stats_t st;
+			gm_stats(ctx, &st);
+			fprintf(stderr, "rnamotif_gpu: batch %d records %lld nt: h2d %.2f ms pack %.2f ms kernel %.2f ms "
+				"d2h %.2f ms sort %.2f ms, %llu candidates, %u retries\n", n_recs, (long long)used,
+				st.h2d_ms, st.pack_ms, st.kernel_ms, st.d2h_ms, st.sort_ms,
+				(unsigned long long)st.n_hits, st.n_retries);
+		}
+
+		/* ---- replay the sink's tail in enumeration order ---- */
+		for (h = 0; h < n_hits;) {
+			const gm_hit_hdr_t *hdr = (const gm_hit_hdr_t *)((const char *)hits + h * stride);
+			const uint32_t rec = hdr->rec;
+			const int comp = hdr->comp;
+			REC_T *rp = &recs[rec];
+			char *sb = buf + rp->off, saved;
+			saved = sb[rp->slen];
+			sb[rp->slen] = '\0';
+			if (comp) {
+				if (rp->slen + 1 > rc_cap) {
+					rc_cap = rp->slen + 1;
+					rcbuf = realloc(rcbuf, rc_cap);
+					if (rcbuf == NULL) {
+						fprintf(stderr, "rnamotif_gpu: out of memory\n");
+						exit(1);
+					}
+				}
+				revcomp_into(sb, rp->slen, rcbuf);
+				GM_replay_strand(rp->sid, rp->sdef, 1, rp->slen, rcbuf);
+			} else
+				GM_replay_strand(rp->sid, rp->sdef, 0, rp->slen, sb);
+			for (; h < n_hits; h++) {
+				hdr = (const gm_hit_hdr_t *)((const char *)hits + h * stride);
+				if (hdr->rec != rec || hdr->comp != comp)
+					break;
+				GM_replay_hit(hdr, (const gm_hit_el_t *)(hdr + 1));
+			}
+			sb[rp->slen] = saved;
+		}
+		for (r = 0; r < n_recs; r++) {
+			free(recs[r].sid);
+			free(recs[r].sdef);
+		}
+	}
+
+	RM_setprog(P_END);
+	RM_score(0, 0, NULL, NULL);
+	gm_ctx_destroy(ctx);
+	exit(0);
+}

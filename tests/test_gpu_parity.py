@@ -1,0 +1,97 @@
+"""-m gpu: the CUDA search (through the C ABI of libgpumotif.so) against the
+oracle port on the same seeded inputs, and against the committed golden
+candidate streams of the reference binary.  Bar: bit-exact (integer work)."""
+import numpy as np
+import pytest
+
+from rnamotif_b200 import gpumotif, oracle_port, synth
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+NAMES = helpers.golden_names()
+
+
+@pytest.fixture(scope="module")
+def db():
+    return synth.golden_db()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_matches_reference_golden(name, db):
+    ids, seq, off = db
+    plan = helpers.load_plan(name)
+    why = gpumotif.plan_check(plan)
+    if why is not None:
+        pytest.skip("plan not supported on the device: " + why)
+    ms = gpumotif.MotifSearch(plan)
+    hits = ms.find_motif(seq, off)
+    st = ms.stats()
+    ms.close()
+    assert st.n_launches >= 1
+    head, els = helpers.hits_to_rows(hits)
+    ghead, gels, gctx = helpers.load_cands(name)
+    assert len(head) == len(ghead), f"{name}: GPU {len(head)} vs reference {len(ghead)} candidates"
+    if len(head):
+        assert (head == ghead[:, :3]).all(), f"{name}: (rec, comp, szero) differ"
+        assert (els == gels).all(), f"{name}: element assignments differ"
+        if gctx.shape[1] == 4:
+            assert (helpers.ctx_rows(hits) == gctx).all(), f"{name}: context differs"
+
+
+@pytest.mark.parametrize("name", ["trna", "pk1", "qu+tr", "pk_j1+2", "score.1", "nanlin", "getbest.strict"])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_gpu_matches_oracle_random(name, seed):
+    plan = helpers.load_plan(name)
+    rng = np.random.default_rng(1000 + seed)
+    lengths = list(rng.integers(0, 3000, size=40)) + [70000]
+    ids, seq, off = synth.random_records(seed, lengths, planted=True, iupac_rate=0.002)
+    both = bool(gpumotif.plan_field(plan, 8))
+    ref, _ = oracle_port.scan_db(plan, seq, off, both)
+    ms = gpumotif.MotifSearch(plan)
+    hits = ms.find_motif(seq, off)
+    ms.close()
+    helpers.assert_same_hits(hits, ref, name)
+
+
+def test_tile_and_range_invariance(db):
+    """Halo chunking: any tile size and any split of the start range gives the
+    same candidates as one pass (SURVEY section 5 'long sequences')."""
+    ids, seq, off = db
+    plan = helpers.load_plan("trna")
+    ms = gpumotif.MotifSearch(plan)
+    ms.upload(seq, off)
+    base = ms.scan()
+    for tile in (32, 100, 777, 4096):
+        ms.set_tile(tile)
+        helpers.assert_same_hits(ms.scan(), base, f"tile {tile}")
+    ms.set_tile(2048)
+    total = ms.total_nt
+    cuts = [0, 1, 63, 5000, 77777, total]
+    parts = [ms.scan(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    merged = np.concatenate(parts)
+    order = np.lexsort((merged["seq"], merged["szero"], merged["comp"], merged["rec"]))
+    helpers.assert_same_hits(merged[order], base, "range split")
+    ms.close()
+
+
+def test_hit_buffer_overflow_is_recovered(db):
+    ids, seq, off = db
+    plan = helpers.load_plan("getbest")
+    ms = gpumotif.MotifSearch(plan)
+    ms.upload(seq, off)
+    base = ms.scan()
+    assert len(base) > 64
+    ms.set_hit_capacity(16)
+    again = ms.scan()
+    assert ms.stats().n_retries >= 1
+    helpers.assert_same_hits(again, base, "after overflow")
+    ms.close()
+
+
+def test_empty_and_tiny_inputs():
+    plan = helpers.load_plan("trna")
+    ms = gpumotif.MotifSearch(plan)
+    assert len(ms.find_motif(np.zeros(0, np.uint8), np.array([0], np.int64))) == 0
+    assert len(ms.find_motif(np.frombuffer(b"acgu", np.uint8), np.array([0, 0, 4, 4], np.int64))) == 0
+    ms.close()

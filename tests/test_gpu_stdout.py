@@ -1,0 +1,52 @@
+"""-m gpu: byte-identical rnamotif stdout.  rnamotif_gpu (reference front end +
+score/efn/printer on the host, search in libgpumotif) against
+  (a) the committed md5 of the reference binary's raw stdout for each of the
+      24 `make test` command lines (tests/golden/make_test_md5.json; the same
+      runs pass the reference's test/*.chk goldens, oracle/check_goldens.sh), and
+  (b) the reference binary itself (oracle/_ref/rnamotif), run side by side.
+Needs the prebuilt programs and test inputs under oracle/_ref/ and
+rnamotif_b200/host/_build/ (they travel with the snapshot)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+GPU_BIN = os.path.join(helpers.ROOT, "rnamotif_b200", "host", "_build", "rnamotif_gpu")
+REF_BIN = os.path.join(helpers.REF, "rnamotif")
+DATA = os.path.join(helpers.REF, "data")
+MD5 = json.load(open(os.path.join(helpers.GOLDEN, "make_test_md5.json")))
+
+have = os.path.exists(GPU_BIN) and os.path.exists(os.path.join(DATA, "test", "gbrna.111.0.fastn"))
+
+
+def run(binary, name, extra_env=None):
+    flags = ["-sh", "-context", "-Dctx_maxlen=5"] if name.endswith(".strict") else []
+    env = dict(os.environ, EFNDATA=os.path.join(DATA, "efndata"))
+    env.update(extra_env or {})
+    r = subprocess.run([binary, *flags, "-descr", name + ".descr", "gbrna.111.0.fastn"],
+                       cwd=os.path.join(DATA, "test"), env=env, capture_output=True, timeout=1200)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")[-2000:]
+    return r.stdout
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref or rnamotif_gpu not built")
+@pytest.mark.parametrize("name", sorted(MD5))
+def test_make_test_stdout_md5(name):
+    out = run(GPU_BIN, name)
+    assert out.count(b"\n>") + out.startswith(b">") >= 0
+    assert hashlib.md5(out).hexdigest() == MD5[name]["md5"], f"{name}: stdout differs from the reference"
+
+
+@pytest.mark.skipif(not (have and os.path.exists(REF_BIN)), reason="reference binary not built")
+@pytest.mark.parametrize("name", ["trna", "pk1", "qu+tr.strict", "getbest"])
+def test_stdout_equals_reference_binary_small_batches(name):
+    # small batches: records split across many uploads, score state carried across
+    out = run(GPU_BIN, name, {"GPUMOTIF_BATCH_NT": "300000"})
+    ref = run(REF_BIN, name)
+    assert out == ref
