@@ -1,4 +1,23 @@
-// gm_machine.cuh -- gm_search_kernel: tile staging + the search machine.
+// gm_machine.cuh -- gm_search_kernel: tile staging, span-end prefilter, and
+// the search machine.
+//
+// Per tile (TILE consecutive nucleotides of the concatenated database, both
+// strands):
+//   1. one TMA bulk copy brings the packed tile + halo into shared memory;
+//      it is expanded to one byte per nucleotide for the forward strand and
+//      for the reverse complement (mk_rcmp, src/rnamot.c:193-216);
+//   2. "pair bitsets" are built with __ballot_sync: for every distinct duplex
+//      table D used by a helix head and every base x, bit p of P[D][x] says
+//      whether x pairs with the nucleotide at tile position p.  With them the
+//      set of span ends whose outermost `req` pairs can form is a handful of
+//      funnel shifts and ANDs (wc_mask) instead of a loop over span ends;
+//   3. warps pull chunks of 32 start positions; a start whose level-0 mask is
+//      empty (or whose anchored seq= cannot match) is dropped at once, the
+//      others go to a small per-warp queue;
+//   4. lanes take starts from the queue and run the explicit-stack machine.
+//      The masks are hints that only ever remove span ends match_wchlx would
+//      reject at its first tests (src/find_motif.c:1010-1079); every survivor
+//      goes through the full test, so the enumeration is unchanged.
 #pragma once
 
 #include "gm_kernel.cuh"
@@ -10,13 +29,17 @@ enum {
 	PH_SS_RESUME = 16, PH_WX_RESUME, PH_PH_RESUME, PH_TR_RESUME, PH_QU_RESUME
 };
 
-// frame word 3, low half: mpr (8 bits) | l_bpr << 8 | chk << 9
-#define FR3_LO(mpr, lbpr, chk) (((mpr) & 0xff) | ((lbpr) << 8) | ((chk) << 9))
+// frame word 1, low half: mpr (8 bits) | l_bpr << 8 | chk << 9
+#define FR1_LO(mpr, lbpr, chk) (((mpr) & 0xff) | ((lbpr) << 8) | ((chk) << 9))
+
+#define GM_QCAP 128 // per-warp queue of start items (power of two)
 
 struct Smem {
 	uint64_t bar;
-	int work;          // next work item of the current tile
-	int r_lo, r_n;     // records intersecting the tile: first index, count (0 = use global table)
+	int work;          // next chunk of start items of the current tile
+	int r_lo;          // first record intersecting the tile
+	int one_rec;       // the tile lies inside a single record
+	int pad;
 	int64_t tile;      // current tile index (broadcast)
 };
 
@@ -36,26 +59,78 @@ __device__ __forceinline__ uint8_t complement_byte(uint8_t v)
 	return (uint8_t)((1u << nb) | (nb << 4));
 }
 
+// 64 bits of a bitset starting at bit q (q >= 0; the set is padded by 4 words)
+__device__ __forceinline__ uint64_t bits64(const uint32_t *set, int q)
+{
+	const int w = q >> 5, sh = q & 31;
+	const uint32_t a = set[w], b = set[w + 1], c = set[w + 2];
+	const uint32_t lo = __funnelshift_r(a, b, sh);
+	const uint32_t hi = __funnelshift_r(b, c, sh);
+	return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+struct PairBits {
+	const uint32_t *base;  // [strand][dup][x][nwb]
+	int nwb;               // words per bitset
+	int n_dups;
+};
+
+// Span ends s3 in [lo, lo+n) (n <= 64) at which the helix whose 5' strand
+// starts at window position z can have its first `req` pairs formed with at
+// most `budget` mispairs -- a superset of the span ends match_wchlx accepts.
+// bit j of the result <-> s3 = lo + j.
+__device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
+	int dupi, int flt, int z, int lo, int n)
+{
+	const uint64_t ones = n >= 64 ? ~0ull : ((1ull << n) - 1);
+	const int req = flt & 0xff, budget = (flt >> 8) & 0xff, first_must = (flt >> 16) & 1;
+	if (dupi < 0 || req == 0)
+		return ones;
+	const uint32_t *sets = pb.base + ((size_t)(strand * pb.n_dups + dupi) * 4) * pb.nwb;
+	uint64_t a0 = ones, a1 = ones, a2 = ones;
+	for (int k = 0; k < req; k++) {
+		const int x = bcode_of(sq[z + k]);
+		uint64_t m = 0;
+		if (x < 4)
+			m = bits64(sets + x * pb.nwb, sqbase + lo - k);
+		if (k == 0) {
+			if (first_must)
+				a0 = a1 = a2 = m;
+			// else: an outermost mispair is always tolerated (ends without 5'
+			// pairing, src/find_motif.c:1014-1017): no constraint from k = 0
+		} else {
+			a2 = (a2 & m) | a1;
+			a1 = (a1 & m) | a0;
+			a0 &= m;
+		}
+	}
+	return (budget == 0 ? a0 : budget == 1 ? a1 : a2) & ones;
+}
+
 __global__ void gm_search_kernel(const ScanArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, nt = blockDim.x;
-	const int lane = tid & 31;
+	const int lane = tid & 31, warp = tid >> 5;
 	const int NS = c_par.n_searches, ND = c_par.n_descr;
 	const int W = c_par.w_winsize, H = c_par.halo, TILE = c_par.tile;
 	const int Lbytes = (TILE + 2 * H + 15) & ~15;          // nucleotides staged per tile
 	const int stage_bytes = ((Lbytes >> 1) + 32 + 15) & ~15; // packed staging (+ alignment slack)
+	const int nwb = ((Lbytes + 31) >> 5) + 4;
+	const int n_dups = c_par.n_dups;
 
-	// carve shared memory
+	// carve shared memory (mirrors smem_need() on the host)
 	Smem *sm = reinterpret_cast<Smem *>(smem_raw);
 	uint8_t *p = smem_raw + 64;
 	uint8_t *sm_stage = p;               p += stage_bytes;
 	uint8_t *sm_fwd = p;                 p += Lbytes;
 	uint8_t *sm_rc = p;                  p += Lbytes;
+	uint32_t *sm_pb = reinterpret_cast<uint32_t *>(p);         p += (((size_t)2 * n_dups * 4 * nwb * 4) + 15) & ~(size_t)15;
 	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
 	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
 	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
 	int64_t *sm_rec = reinterpret_cast<int64_t *>(p);          p += (GM_REC_CACHE + 1) * 8;
+	uint16_t *sm_q = reinterpret_cast<uint16_t *>(p);          p += (size_t)(nt >> 5) * GM_QCAP * 2;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
 
 	// stage the hot plan tables
@@ -75,6 +150,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	L.ps = sm_ps;
 	L.NS = NS;
 	L.ND = ND;
+	L.el_base = NS + c_par.frame_words;
 	L.sq = sm_fwd;
 	L.szero = L.slen = L.comp = 0;
 	L.rec = 0;
@@ -85,10 +161,16 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		unmark(L, d);
 		set_cnt(L, d, GM_UNDEF, GM_UNDEF);
 	}
+	PairBits pb;
+	pb.base = sm_pb;
+	pb.nwb = nwb;
+	pb.n_dups = n_dups;
+	uint16_t *myq = sm_q + warp * GM_QCAP;
 	__syncthreads();
 
 	uint32_t parity = 0;
 	unsigned long long my_starts = 0;
+	int sqbase = 0, strand = 0; // tile index of the lane's window start, strand buffer
 
 	for (;;) {
 		// ---- next tile ------------------------------------------------
@@ -109,7 +191,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		if (tid == 0) {
 			mbar_expect_tx(&sm->bar, nbytes);
 			tma_bulk_g2s(sm_stage, A.packed + bs, nbytes, &sm->bar);
-			// records intersecting [gA, gB): binary search for the one holding gA
+			// the last record starting at or before gA
 			int a = 0, b = A.n_rec; // rec_off[a] <= gA < rec_off[b]
 			while (b - a > 1) {
 				int m = (a + b) >> 1;
@@ -118,10 +200,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				else
 					b = m;
 			}
-			// skip empty records that start exactly at gA
-			while (a + 1 < A.n_rec && A.rec_off[a + 1] <= gA)
-				a++;
 			sm->r_lo = a;
+			sm->one_rec = A.rec_off[a + 1] >= gB;
 			sm->work = 0;
 		}
 		__syncthreads();
@@ -147,80 +227,157 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			sm_rc[Lbytes - 1 - i] = complement_byte(v);
 		}
 		__syncthreads();
+		// pair bitsets: one ballot per (strand, table, base) and 32 positions
+		for (int w = warp; w < nwb; w += (nt >> 5)) {
+			const int i = w * 32 + lane;
+			const int vf = i < Lbytes ? bcode_of(sm_fwd[i]) : 4;
+			const int vr = i < Lbytes ? bcode_of(sm_rc[i]) : 4;
+			for (int dd = 0; dd < n_dups; dd++) {
+				const unsigned dup = c_par.dups[dd];
+				for (int x = 0; x < 4; x++) {
+					const unsigned bf = __ballot_sync(0xffffffffu, (dup >> (x * 5 + vf)) & 1u);
+					const unsigned br = __ballot_sync(0xffffffffu, (dup >> (x * 5 + vr)) & 1u);
+					if (lane == 0) {
+						sm_pb[((size_t)(0 * n_dups + dd) * 4 + x) * nwb + w] = bf;
+						sm_pb[((size_t)(1 * n_dups + dd) * 4 + x) * nwb + w] = br;
+					}
+				}
+			}
+		}
+		__syncthreads();
 
 		const int n_work = A.strands * TILE;
+		const bool one_rec = sm->one_rec != 0;
+		const int64_t rec0_off = sm_rec[0];
+		const int rec0_len = (int)(sm_rec[1] - sm_rec[0]);
 		int s = 0, ph = PH_IDLE;
 		bool exhausted = false;
+		int qhead = 0, qtail = 0; // warp-uniform
+
+		// locate start item q: returns false if it is not a start of this scan
+		auto locate = [&](int q, int &comp, int &idx, uint32_t &rec, int &slen, int &szero) -> bool {
+			if (q >= n_work)
+				return false;
+			comp = q >= TILE;
+			const int64_t g = gA + (comp ? q - TILE : q);
+			if (g >= gB)
+				return false;
+			int64_t off;
+			if (one_rec) {
+				off = rec0_off;
+				slen = rec0_len;
+				rec = (uint32_t)sm->r_lo;
+			} else if (g < sm_rec[GM_REC_CACHE]) {
+				int a = 0, b = GM_REC_CACHE;
+				while (b - a > 1) {
+					int m = (a + b) >> 1;
+					if (sm_rec[m] <= g)
+						a = m;
+					else
+						b = m;
+				}
+				off = sm_rec[a];
+				slen = (int)(sm_rec[a + 1] - off);
+				rec = (uint32_t)(a + sm->r_lo);
+			} else {
+				int a = sm->r_lo, b = A.n_rec;
+				while (b - a > 1) {
+					int m = (a + b) >> 1;
+					if (A.rec_off[m] <= g)
+						a = m;
+					else
+						b = m;
+				}
+				off = A.rec_off[a];
+				slen = (int)(A.rec_off[a + 1] - off);
+				rec = (uint32_t)a;
+			}
+			const int pos = (int)(g - off);
+			szero = comp ? slen - 1 - pos : pos;
+			idx = (int)(g - lo);
+			// RM_find_motif searches szero in [0, slen - rm_dminlen], src/find_motif.c:184-205
+			return slen - szero >= c_par.dminlen;
+		};
 
 		// ---- the machine ------------------------------------------------
 		for (;;) {
 			const unsigned idle = __ballot_sync(0xffffffffu, ph == PH_IDLE);
 			if (idle) {
-				if (idle == 0xffffffffu && exhausted)
-					break;
-				if (!exhausted) {
-					int base = 0;
-					const int leader = __ffs(idle) - 1;
-					if (lane == leader)
-						base = atomicAdd(&sm->work, __popc(idle));
-					base = __shfl_sync(0xffffffffu, base, leader);
-					if (base + __popc(idle) >= n_work)
+				const int want = __popc(idle);
+				// top the queue up: prefilter chunks of 32 start items
+				while (qtail - qhead < want && !exhausted) {
+					int chunk = 0;
+					if (lane == 0)
+						chunk = atomicAdd(&sm->work, 32);
+					chunk = __shfl_sync(0xffffffffu, chunk, 0);
+					if (chunk >= n_work) {
 						exhausted = true;
-					if (ph == PH_IDLE) {
-						const int q = base + __popc(idle & ((1u << lane) - 1));
-						if (q < n_work) {
-							const int comp = q >= TILE;
-							const int64_t g = gA + (comp ? q - TILE : q);
-							if (g < gB) {
-								// record holding g
-								int a = 0, b = GM_REC_CACHE;
-								int64_t off, nxt;
-								if (g < sm_rec[GM_REC_CACHE]) {
-									while (b - a > 1) {
-										int m = (a + b) >> 1;
-										if (sm_rec[m] <= g)
-											a = m;
-										else
-											b = m;
-									}
-									off = sm_rec[a];
-									nxt = sm_rec[a + 1];
-									a += sm->r_lo;
-								} else {
-									a = sm->r_lo;
-									b = A.n_rec;
-									while (b - a > 1) {
-										int m = (a + b) >> 1;
-										if (A.rec_off[m] <= g)
-											a = m;
-										else
-											b = m;
-									}
-									off = A.rec_off[a];
-									nxt = A.rec_off[a + 1];
-								}
-								const int slen = (int)(nxt - off);
-								const int pos = (int)(g - off);
-								const int szero = comp ? slen - 1 - pos : pos;
-								const int avail = slen - szero;
-								if (avail >= c_par.dminlen && c_par.dminlen > 0) {
-									L.rec = (uint32_t)a;
-									L.slen = slen;
-									L.szero = szero;
-									L.comp = comp;
-									L.seq = 0;
-									const int idx = (int)(g - lo);
-									L.sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
-									// RM_find_motif, src/find_motif.c:184-205
-									L_ZD(L, 0) = pk16(0, min(W, avail) - 1);
-									s = 0;
-									ph = PH_ENTER;
-									my_starts++;
-								}
+						break;
+					}
+					const int q = chunk + lane;
+					int comp, idx, slen, szero;
+					uint32_t rec;
+					bool pass = locate(q, comp, idx, rec, slen, szero);
+					if (pass) {
+						my_starts++;
+						const DevSearch &S0 = sm_ds[0];
+						const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
+						const int base = comp ? Lbytes - 1 - idx : idx;
+						const int dl = min(W, slen - szero) - 1;
+						if (S0.dupi >= 0 && (S0.flt & 0xff)) {
+							// any span end of search 0 at all?
+							int fsd, lsd;
+							if (S0.kind == K_PK) {
+								fsd = dl;
+								lsd = 2 * S0.minlen - 1;
+							} else {
+								fsd = min(dl, S0.maxglen - 1);
+								lsd = S0.minglen - 1;
 							}
+							bool any = false;
+							for (int hi = fsd; hi >= lsd && !any; hi -= 64) {
+								const int l0 = max(lsd, hi - 63);
+								any = wc_mask(pb, sq, comp, base, S0.dupi, S0.flt, 0, l0, hi - l0 + 1) != 0;
+							}
+							pass = any;
+						}
+						if (pass && S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
+							// a seq= without '$' that cannot match the longest
+							// placement cannot match a shorter one
+							pass = rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
 						}
 					}
+					const unsigned pm = __ballot_sync(0xffffffffu, pass);
+					if (pass)
+						myq[(qtail + __popc(pm & ((1u << lane) - 1))) & (GM_QCAP - 1)] = (uint16_t)q;
+					qtail += __popc(pm);
+					__syncwarp();
 				}
+				// hand queued starts to idle lanes
+				const int avail = qtail - qhead;
+				const int rank = __popc(idle & ((1u << lane) - 1));
+				if (ph == PH_IDLE && rank < avail) {
+					const int q = myq[(qhead + rank) & (GM_QCAP - 1)];
+					int comp, idx, slen, szero;
+					uint32_t rec;
+					locate(q, comp, idx, rec, slen, szero);
+					L.rec = rec;
+					L.slen = slen;
+					L.szero = szero;
+					L.comp = comp;
+					L.seq = 0;
+					strand = comp;
+					sqbase = comp ? Lbytes - 1 - idx : idx;
+					L.sq = (comp ? sm_rc : sm_fwd) + sqbase;
+					// RM_find_motif, src/find_motif.c:184-205
+					L_ZD(L, 0) = pk16(0, min(W, slen - szero) - 1);
+					s = 0;
+					ph = PH_ENTER;
+				}
+				qhead += min(avail, want);
+				__syncwarp();
+				if (exhausted && qtail == qhead && __all_sync(0xffffffffu, ph == PH_IDLE))
+					break;
 			}
 
 			switch (ph) {
@@ -250,6 +407,11 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				} else
 					sd = lsd = dl;
 				L_FR(L, s, 0) = pk16(sd + 1, lsd);
+				if (S.kind == K_WC || S.kind == K_QU) {
+					// no candidate mask yet
+					L_FR(L, s, 5) = 0;
+					L_FR(L, s, 6) = 0;
+				}
 				ph = PH_SPAN;
 			}
 			// fall through
@@ -261,23 +423,39 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const uint32_t w0 = L_FR(L, s, 0);
 				int sd = lo16(w0) - 1;
 				const int lsd = hi16(w0);
-				if (sd < lsd) {
-					ph = PH_RET;
-					break;
-				}
-				if (S.kind == K_WC && S.minlen > 0 && (S.ends & GM_5PAIRED)) {
-					// skip span ends whose outermost pair cannot form
-					// (match_wchlx returns 0 at once, src/find_motif.c:1010-1021)
-					const unsigned row = S.duplex >> (bcode_of(L.sq[z]) * 5);
-					while (sd >= lsd && !((row >> bcode_of(L.sq[sd])) & 1u))
-						sd--;
-					if (sd < lsd) {
-						L_FR(L, s, 0) = pk16(sd, lsd);
+				if (S.kind == K_WC || S.kind == K_QU) {
+					// span ends come from the candidate mask.  `top` (= sd here) is
+					// the largest span end no chunk has covered yet; a chunk is
+					// [clo, clo + 63] and bit j of v stands for span end clo + j.
+					uint64_t v = (uint64_t)L_FR(L, s, 5) | ((uint64_t)L_FR(L, s, 6) << 32);
+					int clo = hi16(L_FR(L, s, 4));
+					int top = sd;
+					while (v == 0) {
+						if (top < lsd)
+							break;
+						clo = max(lsd, top - 63);
+						v = wc_mask(pb, L.sq, strand, sqbase, S.dupi, S.flt, z, clo, top - clo + 1);
+						top = clo - 1;
+					}
+					if (v == 0) {
+						L_FR(L, s, 0) = pk16(top + 1, lsd);
 						ph = PH_RET;
 						break;
 					}
+					const int j = 63 - __clzll((long long)v);
+					v &= ~(1ull << j);
+					sd = clo + j;
+					L_FR(L, s, 5) = (uint32_t)v;
+					L_FR(L, s, 6) = (uint32_t)(v >> 32);
+					L_FR(L, s, 4) = pk16(0, clo);
+					L_FR(L, s, 0) = pk16(top + 1, lsd);
+				} else {
+					if (sd < lsd) {
+						ph = PH_RET;
+						break;
+					}
+					L_FR(L, s, 0) = pk16(sd, lsd);
 				}
-				L_FR(L, s, 0) = pk16(sd, lsd);
 				if (S.next_s >= 0)
 					L_ZD(L, S.next_s) = pk16(sd + 1, dl);
 
@@ -295,7 +473,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 						sink(L, A);
 						unmark(L, S.d);
 					} else {
-						L_FR(L, s, 3) = pk16(0, PH_SS_RESUME);
+						L_FR(L, s, 1) = pk16(0, PH_SS_RESUME);
 						s++;
 						ph = PH_ENTER;
 					}
@@ -318,8 +496,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					t3 = (t3 - i_minl) / 2;
 					t3 = min(t3, S.maxlen);
 					const int s3lim = sd - t3 + 1;
-					L_FR(L, s, 1) = pk16(z, sd);
-					L_FR(L, s, 2) = pk16(s3lim, 0);
+					L_FR(L, s, 2) = pk16(z, sd);
+					L_FR(L, s, 3) = pk16(s3lim, 0);
 					ph = S.minlen == 0 ? PH_WX_BEGIN : PH_WX_FIRST;
 					break;
 				}
@@ -374,7 +552,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					mark(L, S.d, z, hlen);
 					mark(L, S.d3, sd - hlen + 1, hlen);
 					L_ZD(L, s + 1) = pk16(z + hlen, sd - hlen);
-					L_FR(L, s, 3) = pk16(0, PH_PH_RESUME);
+					L_FR(L, s, 1) = pk16(0, PH_PH_RESUME);
 					s++;
 					ph = PH_ENTER;
 					break;
@@ -404,6 +582,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 						break;
 					mark(L, S.d, z, hlen);
 					mark(L, dd2, sd - hlen + 1, hlen);
+					L_FR(L, s, 2) = pk16(z, sd);
 					L_FR(L, s, 4) = pk16(sd - e1.minilen - hlen + 1, hlen);
 					ph = PH_TR_S;
 					break;
@@ -414,16 +593,14 @@ __global__ void gm_search_kernel(const ScanArgs A)
 
 			case PH_WX_BEGIN: {
 				// the empty-helix candidate of match_wchlx, src/find_motif.c:986-1006
+				// (gm_plan_check refuses seq= on a minlen=0 helix, so it is unconditional)
 				const DevSearch &S = sm_ds[s];
-				// gm_plan_check refuses seq= on a minlen=0 helix, so the
-				// candidate is unconditional
-				const uint32_t w1 = L_FR(L, s, 1);
-				const int s5 = lo16(w1), s3 = hi16(w1);
-				L_FR(L, s, 3) = pk16(FR3_LO(0, 1, 0), PH_WX_RESUME);
+				const uint32_t w2 = L_FR(L, s, 2);
+				const int s5 = lo16(w2), s3 = hi16(w2);
+				L_FR(L, s, 1) = pk16(FR1_LO(0, 1, 0), PH_WX_RESUME);
 				// after this candidate the first pair is tested: hl stays 0
 				if (S.kind == K_WC) {
-					const int i_len = s3 - s5 + 1;
-					if (i_len > S.maxilen) {
+					if (s3 - s5 + 1 > S.maxilen) {
 						ph = PH_WX_FIRST;
 						break;
 					}
@@ -437,12 +614,10 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				} else if (S.kind == K_QU) {
 					mark(L, S.d, s5, 0);
 					mark(L, S.d3, s3 + 1, 0);
-					L_FR(L, s, 4) = pk16(s5 + S.minilen - 1, 0);
+					L_FR(L, s, 7) = pk16(s5 + S.minilen - 1, 0);
 					ph = PH_QU_S1;
-				} else {
-					// K_PK with minlen 0 is refused by gm_plan_check
-					ph = PH_WX_FIRST;
-				}
+				} else
+					ph = PH_WX_FIRST; // K_PK with minlen 0 is refused by gm_plan_check
 				break;
 			}
 
@@ -450,7 +625,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const DevSearch &S = sm_ds[s];
 				unmark(L, S.d);
 				unmark(L, S.d3);
-				if (hi16(L_FR(L, s, 2)) == 0) {
+				if (hi16(L_FR(L, s, 3)) == 0) {
 					// came back from the empty-helix candidate
 					ph = PH_WX_FIRST;
 					break;
@@ -462,8 +637,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			case PH_WX_EXT: {
 				// match_wchlx, src/find_motif.c:1008-1109, one candidate at a time
 				const DevSearch &S = sm_ds[s];
-				const uint32_t w1 = L_FR(L, s, 1), w2 = L_FR(L, s, 2);
-				const int s5 = lo16(w1), s3 = hi16(w1), s3lim = lo16(w2);
+				const uint32_t w2 = L_FR(L, s, 2), w3 = L_FR(L, s, 3);
+				const int s5 = lo16(w2), s3 = hi16(w2), s3lim = lo16(w3);
 				int hl, mpr, lbpr, chk;
 				if (ph == PH_WX_FIRST) {
 					if (paired(S.duplex, L.sq[s5], L.sq[s3])) {
@@ -476,11 +651,11 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					}
 					chk = 1;
 				} else {
-					const int f3 = lo16(L_FR(L, s, 3));
-					hl = hi16(w2);
-					mpr = f3 & 0xff;
-					lbpr = (f3 >> 8) & 1;
-					chk = (f3 >> 9) & 1;
+					const int f1 = lo16(L_FR(L, s, 1));
+					hl = hi16(w3);
+					mpr = f1 & 0xff;
+					lbpr = (f1 >> 8) & 1;
+					chk = (f1 >> 9) & 1;
 				}
 				int found = 0;
 				for (;;) {
@@ -550,8 +725,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					break;
 				}
 				// a candidate: remember where the extension stands
-				L_FR(L, s, 2) = pk16(s3lim, hl);
-				L_FR(L, s, 3) = pk16(FR3_LO(mpr, lbpr, 0), PH_WX_RESUME);
+				L_FR(L, s, 3) = pk16(s3lim, hl);
+				L_FR(L, s, 1) = pk16(FR1_LO(mpr, lbpr, 0), PH_WX_RESUME);
 				mark(L, S.d, s5, hl);
 				mark(L, S.d3, s3 - hl + 1, hl);
 				if (S.kind == K_WC) {
@@ -568,7 +743,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					ph = PH_ENTER;
 				} else {
 					// find_4plex_inner, src/find_motif.c:937-938
-					L_FR(L, s, 4) = pk16(s5 + hl + S.minilen - 1, 0);
+					L_FR(L, s, 7) = pk16(s5 + hl + S.minilen - 1, 0);
 					ph = PH_QU_S1;
 				}
 				break;
@@ -596,27 +771,46 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					break; // next s5
 				const int f_s3 = sd - s_minl;
 				const int l_s3 = sd - min(slen - g_minl, s_maxl);
-				L_FR(L, s, 1) = pk16(s5, f_s3 + 1);
+				L_FR(L, s, 2) = pk16(s5, f_s3 + 1);
 				L_FR(L, s, 5) = pk16(l_s3, i_minl);
+				L_FR(L, s, 7) = 0;
+				L_FR(L, s, 8) = 0;
+				L_FR(L, s, 6) = pk16(f_s3, 0); // (largest 3' end not yet covered, chunk low end)
 				ph = PH_PK_S3;
 				break;
 			}
 
 			case PH_PK_S3: {
-				// find_pknot3 loop over the 3' end, src/find_motif.c:600-606
+				// find_pknot3 loop over the 3' end, src/find_motif.c:600-606,
+				// through the same candidate mask as the proper helices
 				const DevSearch &S = sm_ds[s];
-				const uint32_t w1 = L_FR(L, s, 1), w5 = L_FR(L, s, 5);
-				const int s5 = lo16(w1), s3 = hi16(w1) - 1;
+				const uint32_t w2 = L_FR(L, s, 2), w5 = L_FR(L, s, 5), w6 = L_FR(L, s, 6);
+				const int s5 = lo16(w2);
 				const int l_s3 = lo16(w5), i_minl = hi16(w5);
-				if (s3 < l_s3) {
+				int top = lo16(w6), clo = hi16(w6);
+				uint64_t v = (uint64_t)L_FR(L, s, 7) | ((uint64_t)L_FR(L, s, 8) << 32);
+				while (v == 0) {
+					if (top < l_s3)
+						break;
+					clo = max(l_s3, top - 63);
+					v = wc_mask(pb, L.sq, strand, sqbase, S.dupi, S.flt, s5, clo, top - clo + 1);
+					top = clo - 1;
+				}
+				if (v == 0) {
 					ph = PH_PK_S5;
 					break;
 				}
-				L_FR(L, s, 1) = pk16(s5, s3);
+				const int j = 63 - __clzll((long long)v);
+				v &= ~(1ull << j);
+				const int s3 = clo + j;
+				L_FR(L, s, 7) = (uint32_t)v;
+				L_FR(L, s, 8) = (uint32_t)(v >> 32);
+				L_FR(L, s, 6) = pk16(top, clo);
+				L_FR(L, s, 2) = pk16(s5, s3);
 				int t3 = s3 - s5 + 1;
 				t3 = (t3 - i_minl) / 2;
 				t3 = min(t3, S.maxlen);
-				L_FR(L, s, 2) = pk16(s3 - t3 + 1, 0);
+				L_FR(L, s, 3) = pk16(s3 - t3 + 1, 0);
 				ph = PH_WX_FIRST;
 				break;
 			}
@@ -631,9 +825,9 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const gm_elem_t &e = c_plan.elems[S.d];
 				const int dd1 = e.mates[0], dd2 = e.mates[1];
 				const gm_elem_t &e1 = c_plan.elems[dd1];
-				const uint32_t w4 = L_FR(L, s, 4);
+				const uint32_t w4 = L_FR(L, s, 4), w2 = L_FR(L, s, 2);
 				const int sp = lo16(w4) - 1, hlen = hi16(w4);
-				const int z = lo16(L_ZD(L, s)), sd = lo16(L_FR(L, s, 0));
+				const int z = lo16(w2), sd = hi16(w2);
 				if (sp < z + 2 * hlen + S.minilen - 1) {
 					unmark(L, S.d);
 					unmark(L, dd2);
@@ -654,7 +848,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				mark(L, dd1, sp - hlen + 1, hlen);
 				L_ZD(L, s + 1) = pk16(z + hlen, sp - hlen);
 				L_ZD(L, c_plan.elems[e1.inner].searchno) = pk16(sp + 1, sd - hlen);
-				L_FR(L, s, 3) = pk16(lo16(L_FR(L, s, 3)), PH_TR_RESUME);
+				L_FR(L, s, 1) = pk16(0, PH_TR_RESUME);
 				s++;
 				ph = PH_ENTER;
 				break;
@@ -666,8 +860,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const gm_elem_t &e = c_plan.elems[S.d];
 				const int i2_minl = c_plan.elems[e.mates[0]].minilen;
 				const int i3_minl = c_plan.elems[e.mates[1]].minilen;
-				const int s3 = hi16(L_FR(L, s, 1)), hl = hi16(L_FR(L, s, 2));
-				const int s1 = lo16(L_FR(L, s, 4)) + 1;
+				const int s3 = hi16(L_FR(L, s, 2)), hl = hi16(L_FR(L, s, 3));
+				const int s1 = lo16(L_FR(L, s, 7)) + 1;
 				if (s1 > s3 - 3 * hl - i3_minl - i2_minl) {
 					// this q1/q4 helix is done: back to the extension
 					unmark(L, S.d);
@@ -675,7 +869,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					ph = hl == 0 ? PH_WX_FIRST : PH_WX_EXT;
 					break;
 				}
-				L_FR(L, s, 4) = pk16(s1, s3 - hl - i3_minl + 1);
+				L_FR(L, s, 7) = pk16(s1, s3 - hl - i3_minl + 1);
 				ph = PH_QU_S2;
 				break;
 			}
@@ -693,14 +887,14 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const gm_elem_t &e = c_plan.elems[S.d];
 				const int dd1 = e.mates[0], dd2 = e.mates[1];
 				const gm_elem_t &e1 = c_plan.elems[dd1], &e2 = c_plan.elems[dd2];
-				const uint32_t w4 = L_FR(L, s, 4);
-				const int s1 = lo16(w4), s2 = hi16(w4) - 1;
-				const int z = lo16(L_FR(L, s, 1)), s3 = hi16(L_FR(L, s, 1)), hl = hi16(L_FR(L, s, 2));
+				const uint32_t w2 = L_FR(L, s, 2), w7 = L_FR(L, s, 7);
+				const int z = lo16(w2), s3 = hi16(w2), hl = hi16(L_FR(L, s, 3));
+				const int s1 = lo16(w7), s2 = hi16(w7) - 1;
 				if (s2 < s1 + 2 * hl + e1.minilen) {
 					ph = PH_QU_S1;
 					break;
 				}
-				L_FR(L, s, 4) = pk16(s1, s2);
+				L_FR(L, s, 7) = pk16(s1, s2);
 				int n_mpr;
 				if (!match_4plex(L, dd1, dd2, z, s1, s2, s3, hl, &n_mpr))
 					break;
@@ -719,7 +913,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				L_ZD(L, s + 1) = pk16(z + hl, s1 - 1);
 				L_ZD(L, c_plan.elems[e1.inner].searchno) = pk16(s1 + hl, s2 - hl);
 				L_ZD(L, c_plan.elems[e2.inner].searchno) = pk16(s2 + 1, s3 - hl);
-				L_FR(L, s, 3) = pk16(lo16(L_FR(L, s, 3)), PH_QU_RESUME);
+				L_FR(L, s, 1) = pk16(lo16(L_FR(L, s, 1)), PH_QU_RESUME);
 				s++;
 				ph = PH_ENTER;
 				break;
@@ -730,7 +924,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					ph = PH_IDLE;
 				else {
 					s--;
-					ph = hi16(L_FR(L, s, 3));
+					ph = hi16(L_FR(L, s, 1));
 				}
 				break;
 			}

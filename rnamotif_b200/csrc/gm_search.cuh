@@ -43,9 +43,13 @@ struct DevSearch {
 	int rx5, rx3;          // regex of head / far strand, or -1
 	int mm5;               // mismatch limit of the head (ss only on the device)
 	int last;              // 1 for the final search (hit sink follows)
-	int pad0, pad1, pad2;
+	int fr;                // word offset of this search's frame in the lane state
+	int dupi;              // index of `duplex` in DevParams::dups (pair bitsets), or -1
+	int flt;               // span-end prefilter: req | budget << 8 | first_must << 16
 };
 static_assert(sizeof(DevSearch) == 23 * 4, "DevSearch is staged with an odd word stride");
+
+#define GM_MAX_DUPS 8
 
 struct DevParams {
 	int n_searches, n_descr;
@@ -55,10 +59,16 @@ struct DevParams {
 	int halo;               // nucleotides staged on each side of a tile
 	int tile;               // starts per tile
 	int words_per_lane;
-	int has_pk;
+	int frame_words;        // sum of all frames
+	int n_dups;             // distinct duplex tables with pair bitsets
+	unsigned dups[GM_MAX_DUPS];
 };
 
-#define GM_FW 6  // frame words per search
+// frame words: 0 (sd, lsd)  1 (flags, resume phase)  2 (s5, s3)  3 (s3lim, hl)
+//              4 kind-specific  5,6 span-end candidate mask (PK: 5 = (l_s3, i_minl), 7,8 = mask)
+#define GM_FW_SS 2
+#define GM_FW_HX 7
+#define GM_FW_PK 9
 
 // phases of the machine
 enum {
@@ -91,6 +101,7 @@ struct Lane {
 	const DevSearch *ds;     // staged search table
 	const gm_pairset_t *ps;  // staged pairsets
 	int NS, ND;
+	int el_base;             // first word of the per-element state
 	// the start this lane is working on
 	int szero;               // absolute offset in the searched strand
 	int slen;                // record length
@@ -101,9 +112,9 @@ struct Lane {
 
 // ---- lane state accessors -------------------------------------------------
 #define L_ZD(L, s)     (L).st[(s) * (L).nt]
-#define L_FR(L, s, k)  (L).st[((L).NS + (s) * GM_FW + (k)) * (L).nt]
-#define L_EL(L, d)     (L).st[((L).NS * (1 + GM_FW) + (d)) * (L).nt]
-#define L_EM(L, d)     (L).st[((L).NS * (1 + GM_FW) + (L).ND + (d)) * (L).nt]
+#define L_FR(L, s, k)  (L).st[((L).NS + (L).ds[s].fr + (k)) * (L).nt]
+#define L_EL(L, d)     (L).st[((L).el_base + (d)) * (L).nt]
+#define L_EM(L, d)     (L).st[((L).el_base + (L).ND + (d)) * (L).nt]
 
 __device__ __forceinline__ void mark(Lane &L, int d, int off, int len)
 {

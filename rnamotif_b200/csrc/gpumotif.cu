@@ -254,7 +254,42 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	par->dminlen = pl->dminlen;
 	par->strict_helices = pl->strict_helices;
 	par->halo = W + cx + 2;
-	par->words_per_lane = NS * (1 + GM_FW) + 2 * ND;
+	// frames, pair-bitset tables and span-end prefilter parameters
+	int fr = 0;
+	for (int s = 0; s < NS; s++) {
+		DevSearch &S = ds[s];
+		S.fr = fr;
+		fr += S.kind == K_SS ? GM_FW_SS : (S.kind == K_PK || S.kind == K_QU) ? GM_FW_PK : GM_FW_HX;
+		S.dupi = -1;
+		S.flt = 0;
+		if (S.kind == K_WC || S.kind == K_QU || S.kind == K_PK) {
+			int k;
+			for (k = 0; k < par->n_dups; k++)
+				if (par->dups[k] == S.duplex)
+					break;
+			if (k == par->n_dups && par->n_dups < GM_MAX_DUPS)
+				par->dups[par->n_dups++] = S.duplex;
+			if (k < par->n_dups) {
+				S.dupi = k;
+				// match_wchlx, src/find_motif.c:1010-1079: the outermost pair must
+				// form when ends has 5' pairing; afterwards a mispair beyond mplim
+				// ends the extension, and nothing shorter than minlen is a candidate
+				const int first_must = (S.ends & GM_5PAIRED) ? 1 : 0;
+				int req = std::min(S.minlen, 8), budget = S.mplim;
+				if (budget > 2) {
+					req = first_must ? 1 : 0;
+					budget = 0;
+				}
+				if (S.minlen == 0)
+					req = 0; // the empty helix is always a candidate
+				if (req == 1 && !first_must)
+					req = 0;
+				S.flt = req | (budget << 8) | (first_must << 16);
+			}
+		}
+	}
+	par->frame_words = fr;
+	par->words_per_lane = NS + fr + 2 * ND;
 	return 0;
 }
 
@@ -273,10 +308,12 @@ static size_t smem_need(const gm_ctx *c, int threads, int tile)
 	size_t n = 64;
 	n += ((Lb >> 1) + 32 + 15) & ~15;
 	n += 2 * (size_t)Lb;
+	n += (((size_t)2 * c->par.n_dups * 4 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15;
 	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
 	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
 	n += (c->par.n_descr * 4 + 15) & ~15;
 	n += (GM_REC_CACHE + 1) * 8;
+	n += (size_t)(threads >> 5) * GM_QCAP * 2;
 	n += (size_t)c->par.words_per_lane * threads * 4;
 	return n;
 }
