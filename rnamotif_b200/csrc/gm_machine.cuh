@@ -24,10 +24,51 @@
 
 namespace gm {
 
-// resume phases: what a level does when its child has been exhausted
+// Phases are grouped into classes (class = phase >> 3).  Each trip round the
+// machine loop runs ONE class: the one most lanes of the warp are waiting in
+// (majority vote).  Lanes of other classes sit the trip out, which lets lanes
+// pile up in a class and then move through the phase cycle as a convoy instead
+// of the warp executing every class with three or four lanes each.
 enum {
-	PH_SS_RESUME = 16, PH_WX_RESUME, PH_PH_RESUME, PH_TR_RESUME, PH_QU_RESUME
+	CL_IDLE = 0, CL_SPAN = 1, CL_WX = 2, CL_PK = 3, CL_TR = 4, CL_QU = 5
 };
+enum {
+	PHX_IDLE = 0,
+	PHX_ENTER = CL_SPAN * 8, PHX_SPAN, PHX_SS_RESUME, PHX_PH_RESUME,
+	PHX_WX_BEGIN = CL_WX * 8, PHX_WX_RESUME, PHX_WX_FIRST, PHX_WX_EXT,
+	PHX_PK_S5 = CL_PK * 8, PHX_PK_S3,
+	PHX_TR_RESUME = CL_TR * 8, PHX_TR_S,
+	PHX_QU_S1 = CL_QU * 8, PHX_QU_RESUME, PHX_QU_S2
+};
+
+#define PH_IDLE PHX_IDLE
+#define PH_ENTER PHX_ENTER
+#define PH_SPAN PHX_SPAN
+#define PH_SS_RESUME PHX_SS_RESUME
+#define PH_PH_RESUME PHX_PH_RESUME
+#define PH_WX_BEGIN PHX_WX_BEGIN
+#define PH_WX_RESUME PHX_WX_RESUME
+#define PH_WX_FIRST PHX_WX_FIRST
+#define PH_WX_EXT PHX_WX_EXT
+#define PH_PK_S5 PHX_PK_S5
+#define PH_PK_S3 PHX_PK_S3
+#define PH_TR_RESUME PHX_TR_RESUME
+#define PH_TR_S PHX_TR_S
+#define PH_QU_S1 PHX_QU_S1
+#define PH_QU_RESUME PHX_QU_RESUME
+#define PH_QU_S2 PHX_QU_S2
+
+// "return": the level is exhausted, its parent resumes (src/find_motif.c: every
+// find_* returns to its caller's loop)
+#define GM_RETURN()                                  \
+	do {                                             \
+		if (s == 0)                                  \
+			ph = PH_IDLE;                            \
+		else {                                       \
+			s--;                                     \
+			ph = hi16(L_FR(L, s, 1));                \
+		}                                            \
+	} while (0)
 
 // frame word 1, low half: mpr (8 bits) | l_bpr << 8 | chk << 9
 #define FR1_LO(mpr, lbpr, chk) (((mpr) & 0xff) | ((lbpr) << 8) | ((chk) << 9))
@@ -380,6 +421,14 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					break;
 			}
 
+			// majority vote over the classes the lanes are waiting in
+			const int cls = ph >> 3;
+			const unsigned peers = __match_any_sync(0xffffffffu, cls);
+			const int vote = cls == CL_IDLE ? 0 : ((__popc(peers) << 4) | cls);
+			const int run_cls = __reduce_max_sync(0xffffffffu, vote) & 15;
+			if (cls != run_cls)
+				continue;
+
 			switch (ph) {
 			case PH_IDLE:
 				break;
@@ -439,7 +488,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					}
 					if (v == 0) {
 						L_FR(L, s, 0) = pk16(top + 1, lsd);
-						ph = PH_RET;
+						GM_RETURN();
 						break;
 					}
 					const int j = 63 - __clzll((long long)v);
@@ -451,7 +500,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					L_FR(L, s, 0) = pk16(top + 1, lsd);
 				} else {
 					if (sd < lsd) {
-						ph = PH_RET;
+						GM_RETURN();
 						break;
 					}
 					L_FR(L, s, 0) = pk16(sd, lsd);
@@ -919,14 +968,6 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				break;
 			}
 
-			case PH_RET:
-				if (s == 0)
-					ph = PH_IDLE;
-				else {
-					s--;
-					ph = hi16(L_FR(L, s, 1));
-				}
-				break;
 			}
 		}
 		__syncthreads(); // everyone is done with this tile's shared memory

@@ -70,12 +70,6 @@ struct DevParams {
 #define GM_FW_HX 7
 #define GM_FW_PK 9
 
-// phases of the machine
-enum {
-	PH_IDLE = 0, PH_ENTER, PH_SPAN, PH_WX_BEGIN, PH_WX_FIRST, PH_WX_EXT,
-	PH_PK_S5, PH_PK_S3, PH_TR_S, PH_QU_S1, PH_QU_S2, PH_RET
-};
-
 __device__ __forceinline__ uint32_t pk16(int a, int b)
 {
 	return (uint32_t)(a & 0xffff) | ((uint32_t)b << 16);
