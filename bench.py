@@ -201,6 +201,8 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
 
     ms = gpumotif.MotifSearch(plan, device=local)
+    if args.tile:
+        ms.set_tile(args.tile)
     stream = torch.cuda.ExternalStream(ms.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -321,6 +323,7 @@ def main():
     ap.add_argument("--descr", default="trna")
     ap.add_argument("--mnt", type=int, default=1024, help="Mnt of synthetic sequence per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tile", type=int, default=0, help="starts per tile (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -330,6 +330,46 @@ __device__ __forceinline__ int chk_seq5(Lane &L, const DevSearch &S, int off, in
 	return rx_match(rx, L.sq + off, len);
 }
 
+// match_wchlx, src/find_motif.c:1008-1109, as a generator: advance the helix
+// (s5, s3) from its current length hl (0 = nothing tested yet) to the next
+// length that passes match_wchlx's own acceptance tests.  false = the
+// extension is over.
+__device__ __forceinline__ bool wx_next(const Lane &L, const DevSearch &S, int s5, int s3, int s3lim,
+	int &hl, int &mpr, int &lbpr)
+{
+	bool chk = false;
+	if (hl == 0) {
+		if (paired(S.duplex, L.sq[s5], L.sq[s3])) {
+			hl = 1; mpr = 0; lbpr = 1;
+		} else if (!(S.ends & GM_5PAIRED)) {
+			hl = 1; mpr = 1; lbpr = 0;
+		} else
+			return false;
+		chk = true;
+	}
+	for (;;) {
+		if (chk) {
+			if (hl >= S.minlen &&
+			    !(!lbpr && (S.ends & GM_3PAIRED)) &&
+			    !(S.pfrac && mpr > c_plan.lentab[S.lentab + hl]) &&
+			    !(S.rx5 >= 0 && !rx_match(c_plan.regex[S.rx5], L.sq + s5, hl)) &&
+			    !(S.rx3 >= 0 && !rx_match(c_plan.regex[S.rx3], L.sq + s3 - hl + 1, hl)))
+				return true;
+		}
+		if (s3 - hl + 1 < s3lim || hl >= S.maxlen)
+			return false;
+		if (paired(S.duplex, L.sq[s5 + hl], L.sq[s3 - hl]))
+			lbpr = 1;
+		else {
+			if (++mpr > S.mplim)
+				return false;
+			lbpr = 0;
+		}
+		hl++;
+		chk = true;
+	}
+}
+
 // find_minlen / find_maxlen, src/find_motif.c:642-665
 __device__ int pk_minlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
 {

@@ -34,7 +34,7 @@ enum {
 };
 enum {
 	PHX_IDLE = 0,
-	PHX_ENTER = CL_SPAN * 8, PHX_SPAN, PHX_SS_RESUME, PHX_PH_RESUME,
+	PHX_ENTER = CL_SPAN * 8, PHX_SPAN, PHX_SS_RESUME, PHX_PH_RESUME, PHX_WC_RESUME,
 	PHX_WX_BEGIN = CL_WX * 8, PHX_WX_RESUME, PHX_WX_FIRST, PHX_WX_EXT,
 	PHX_PK_S5 = CL_PK * 8, PHX_PK_S3,
 	PHX_TR_RESUME = CL_TR * 8, PHX_TR_S,
@@ -46,6 +46,7 @@ enum {
 #define PH_SPAN PHX_SPAN
 #define PH_SS_RESUME PHX_SS_RESUME
 #define PH_PH_RESUME PHX_PH_RESUME
+#define PH_WC_RESUME PHX_WC_RESUME
 #define PH_WX_BEGIN PHX_WX_BEGIN
 #define PH_WX_RESUME PHX_WX_RESUME
 #define PH_WX_FIRST PHX_WX_FIRST
@@ -429,9 +430,17 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			if (cls != run_cls)
 				continue;
 
+			int wc_stage = 0; // 0: pick the next span end, 1: keep extending the helix
 			switch (ph) {
 			case PH_IDLE:
 				break;
+
+			case PH_WC_RESUME:
+				unmark(L, sm_ds[s].d);
+				unmark(L, sm_ds[s].d3);
+				wc_stage = 1;
+				ph = PH_SPAN;
+				goto do_span;
 
 			case PH_SS_RESUME:
 				unmark(L, sm_ds[s].d);
@@ -455,6 +464,11 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					lsd = z + S.minglen - 1;
 				} else
 					sd = lsd = dl;
+				if (S.kind == K_SS) {
+					// find_ss accepts lengths in [minlen, maxlen] only, src/find_motif.c:349
+					sd = min(sd, z + S.maxlen - 1);
+					lsd = max(lsd, z + S.minlen - 1);
+				}
 				L_FR(L, s, 0) = pk16(sd + 1, lsd);
 				if (S.kind == K_WC || S.kind == K_QU) {
 					// no candidate mask yet
@@ -472,6 +486,111 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const uint32_t w0 = L_FR(L, s, 0);
 				int sd = lo16(w0) - 1;
 				const int lsd = hi16(w0);
+
+				if (S.kind == K_SS) {
+					// find_motif's span loop + find_ss (src/find_motif.c:268-280,332-398)
+					// fused: run down the span ends to the next one that is accepted
+					for (;; sd--) {
+						if (sd < lsd) {
+							GM_RETURN();
+							break;
+						}
+						const int len = sd - z + 1;
+						set_cnt(L, S.d, 0, 0);
+						if (S.rx5 >= 0 && !chk_seq5(L, S, z, len))
+							continue;
+						mark(L, S.d, z, len);
+						if (S.next_s >= 0)
+							L_ZD(L, S.next_s) = pk16(sd + 1, dl);
+						if (S.last) {
+							sink(L, A);
+							unmark(L, S.d);
+							continue;
+						}
+						L_FR(L, s, 0) = pk16(sd, lsd);
+						L_FR(L, s, 1) = pk16(0, PH_SS_RESUME);
+						s++;
+						ph = PH_ENTER;
+						break;
+					}
+					break;
+				}
+
+				if (S.kind == K_WC) {
+					// find_motif's span loop + find_wchlx + match_wchlx
+					// (src/find_motif.c:268-280,400-463,975-1112) fused: one trip =
+					// advance to the next helix candidate of this level, or return
+					const int s5 = z;
+					int top = sd, clo = hi16(L_FR(L, s, 4));
+					uint64_t v = (uint64_t)L_FR(L, s, 5) | ((uint64_t)L_FR(L, s, 6) << 32);
+					int s3 = 0, s3lim = 0, hl = 0, mpr = 0, lbpr = 1;
+					if (wc_stage) {
+						const uint32_t w3 = L_FR(L, s, 3);
+						const int f1 = lo16(L_FR(L, s, 1));
+						s3 = hi16(L_FR(L, s, 2));
+						s3lim = lo16(w3);
+						hl = hi16(w3);
+						mpr = f1 & 0xff;
+						lbpr = (f1 >> 8) & 1;
+					}
+					for (;;) {
+						bool cand = false;
+						if (!wc_stage) {
+							// next span end from the candidate mask: `top` is the largest
+							// span end no chunk has covered; bit j of v <-> clo + j
+							while (v == 0) {
+								if (top < lsd)
+									break;
+								clo = max(lsd, top - 63);
+								v = wc_mask(pb, L.sq, strand, sqbase, S.dupi, S.flt, z, clo, top - clo + 1);
+								top = clo - 1;
+							}
+							if (v == 0) {
+								GM_RETURN();
+								break;
+							}
+							const int j = 63 - __clzll((long long)v);
+							v &= ~(1ull << j);
+							s3 = clo + j;
+							int t3 = s3 - z + 1;
+							t3 = (t3 - S.minilen) / 2;
+							t3 = min(t3, S.maxlen);
+							s3lim = s3 - t3 + 1;
+							hl = 0; mpr = 0; lbpr = 1;
+							wc_stage = 1;
+							// the empty helix (minlen = 0) comes first, src/find_motif.c:986-1006
+							cand = S.minlen == 0 && s3 - s5 + 1 <= S.maxilen;
+						}
+						if (!cand) {
+							if (!wx_next(L, S, s5, s3, s3lim, hl, mpr, lbpr)) {
+								wc_stage = 0;
+								continue;
+							}
+							// find_wchlx, src/find_motif.c:441-447
+							if (s3 - s5 - 2 * hl + 1 > S.maxilen)
+								continue;
+						}
+						// descend into the interior with this helix
+						L_FR(L, s, 0) = pk16(top + 1, lsd);
+						L_FR(L, s, 1) = pk16(FR1_LO(mpr, lbpr, 0), PH_WC_RESUME);
+						L_FR(L, s, 2) = pk16(s5, s3);
+						L_FR(L, s, 3) = pk16(s3lim, hl);
+						L_FR(L, s, 4) = pk16(0, clo);
+						L_FR(L, s, 5) = (uint32_t)v;
+						L_FR(L, s, 6) = (uint32_t)(v >> 32);
+						set_cnt(L, S.d, mpr, 0);
+						set_cnt(L, S.d3, mpr, 0);
+						mark(L, S.d, s5, hl);
+						mark(L, S.d3, s3 - hl + 1, hl);
+						if (S.next_s >= 0)
+							L_ZD(L, S.next_s) = pk16(s3 + 1, dl);
+						L_ZD(L, s + 1) = pk16(s5 + hl, s3 - hl);
+						s++;
+						ph = PH_ENTER;
+						break;
+					}
+					break;
+				}
 				if (S.kind == K_WC || S.kind == K_QU) {
 					// span ends come from the candidate mask.  `top` (= sd here) is
 					// the largest span end no chunk has covered yet; a chunk is
