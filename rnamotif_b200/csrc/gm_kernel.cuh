@@ -38,7 +38,15 @@ struct ScanArgs {
 	uint32_t *hits;             // hit records, stride_words each
 	unsigned long long hit_cap;
 	int stride_words;
+	// worklist of starts that survived the level-0 prefilter (split path):
+	// GM_WL_WORDS words per entry, see gm_prefilter_kernel
+	uint32_t *wl;
+	unsigned long long *wl_count;   // entries appended by gm_prefilter_kernel
+	unsigned long long *wl_head;    // entries handed out by gm_dfs_kernel
+	unsigned long long wl_cap;
 };
+
+#define GM_WL_WORDS 8
 
 // ---------------------------------------------------------------- packing
 

@@ -149,6 +149,12 @@ __device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, i
 	return (budget == 0 ? a0 : budget == 1 ? a1 : a2) & ones;
 }
 
+// MODE 0: fused -- prefilter and machine in one kernel, lanes refilled from a
+//         per-warp queue, one tile at a time (works for every plan).
+// MODE 1: prefilter only -- survivors are appended to a global worklist that
+//         gm_dfs_kernel consumes (the split path: no tile barrier ever waits
+//         for a long enumeration, and the worklist rebalances the starts).
+template <int MODE>
 __global__ void gm_search_kernel(const ScanArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -199,9 +205,11 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	L.seq = 0;
 	// never-marked elements read as UNDEF; counters start at UNDEF like
 	// SE_init leaves them (src/compile.c:570-571)
-	for (int d = 0; d < ND; d++) {
-		unmark(L, d);
-		set_cnt(L, d, GM_UNDEF, GM_UNDEF);
+	if (MODE == 0) {
+		for (int d = 0; d < ND; d++) {
+			unmark(L, d);
+			set_cnt(L, d, GM_UNDEF, GM_UNDEF);
+		}
 	}
 	PairBits pb;
 	pb.base = sm_pb;
@@ -341,6 +349,90 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			return slen - szero >= c_par.dminlen;
 		};
 
+		// level-0 prefilter of start item q.  v0/have_v0: the candidate mask of
+		// search 0's span ends when they all fit one 64-wide chunk.
+		auto prefilter = [&](int q, uint64_t &v0, int &have_v0) -> bool {
+			int comp, idx, slen, szero;
+			uint32_t rec;
+			v0 = 0;
+			have_v0 = 0;
+			bool pass = locate(q, comp, idx, rec, slen, szero);
+			if (!pass)
+				return false;
+			my_starts++;
+			const DevSearch &S0 = sm_ds[0];
+			const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
+			const int base = comp ? Lbytes - 1 - idx : idx;
+			const int dl = min(W, slen - szero) - 1;
+			if (S0.dupi >= 0 && (S0.flt & 0xff)) {
+				// any span end of search 0 at all?
+				int fsd, lsd;
+				if (S0.kind == K_PK) {
+					fsd = dl;
+					lsd = 2 * S0.minlen - 1;
+				} else {
+					fsd = min(dl, S0.maxglen - 1);
+					lsd = S0.minglen - 1;
+				}
+				bool any = false;
+				for (int hi = fsd; hi >= lsd && !any; hi -= 64) {
+					const int l0 = max(lsd, hi - 63);
+					const uint64_t v = wc_mask(pb, sq, comp, base, S0.dupi, S0.flt, 0, l0, hi - l0 + 1);
+					any = v != 0;
+					if (hi == fsd && l0 == lsd && S0.kind != K_PK) {
+						v0 = v;
+						have_v0 = 1;
+					}
+				}
+				pass = any;
+			}
+			if (pass && S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
+				// a seq= without '$' that cannot match the longest
+				// placement cannot match a shorter one
+				pass = rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
+			}
+			return pass;
+		};
+
+		if (MODE == 1) {
+			// prefilter only: append the survivors to the global worklist
+			for (;;) {
+				int chunk = 0;
+				if (lane == 0)
+					chunk = atomicAdd(&sm->work, 32);
+				chunk = __shfl_sync(0xffffffffu, chunk, 0);
+				if (chunk >= n_work)
+					break;
+				const int q = chunk + lane;
+				uint64_t v0;
+				int have_v0;
+				const bool pass = prefilter(q, v0, have_v0);
+				const unsigned pm = __ballot_sync(0xffffffffu, pass);
+				if (pm == 0)
+					continue;
+				unsigned long long base = 0;
+				const int leader = __ffs(pm) - 1;
+				if (lane == leader)
+					base = atomicAdd(A.wl_count, (unsigned long long)__popc(pm));
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if (pass) {
+					const unsigned long long slot = base + __popc(pm & ((1u << lane) - 1));
+					if (slot < A.wl_cap) {
+						int comp, idx, slen, szero;
+						uint32_t rec;
+						locate(q, comp, idx, rec, slen, szero);
+						const int64_t g = lo + idx;
+						uint4 *e = reinterpret_cast<uint4 *>(A.wl + slot * GM_WL_WORDS);
+						e[0] = make_uint4((uint32_t)g, (uint32_t)(g >> 32) | ((uint32_t)comp << 31) |
+							((uint32_t)have_v0 << 30), rec, (uint32_t)slen);
+						e[1] = make_uint4((uint32_t)szero, (uint32_t)v0, (uint32_t)(v0 >> 32), 0u);
+					}
+				}
+			}
+			__syncthreads();
+			continue;
+		}
+
 		// ---- the machine ------------------------------------------------
 		for (;;) {
 			const unsigned idle = __ballot_sync(0xffffffffu, ph == PH_IDLE);
@@ -357,38 +449,9 @@ __global__ void gm_search_kernel(const ScanArgs A)
 						break;
 					}
 					const int q = chunk + lane;
-					int comp, idx, slen, szero;
-					uint32_t rec;
-					bool pass = locate(q, comp, idx, rec, slen, szero);
-					if (pass) {
-						my_starts++;
-						const DevSearch &S0 = sm_ds[0];
-						const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
-						const int base = comp ? Lbytes - 1 - idx : idx;
-						const int dl = min(W, slen - szero) - 1;
-						if (S0.dupi >= 0 && (S0.flt & 0xff)) {
-							// any span end of search 0 at all?
-							int fsd, lsd;
-							if (S0.kind == K_PK) {
-								fsd = dl;
-								lsd = 2 * S0.minlen - 1;
-							} else {
-								fsd = min(dl, S0.maxglen - 1);
-								lsd = S0.minglen - 1;
-							}
-							bool any = false;
-							for (int hi = fsd; hi >= lsd && !any; hi -= 64) {
-								const int l0 = max(lsd, hi - 63);
-								any = wc_mask(pb, sq, comp, base, S0.dupi, S0.flt, 0, l0, hi - l0 + 1) != 0;
-							}
-							pass = any;
-						}
-						if (pass && S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
-							// a seq= without '$' that cannot match the longest
-							// placement cannot match a shorter one
-							pass = rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
-						}
-					}
+					uint64_t v0;
+					int have_v0;
+					const bool pass = prefilter(q, v0, have_v0);
 					const unsigned pm = __ballot_sync(0xffffffffu, pass);
 					if (pass)
 						myq[(qtail + __popc(pm & ((1u << lane) - 1))) & (GM_QCAP - 1)] = (uint16_t)q;
@@ -422,672 +485,9 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					break;
 			}
 
-			// majority vote over the classes the lanes are waiting in
-			const int cls = ph >> 3;
-			const unsigned peers = __match_any_sync(0xffffffffu, cls);
-			const int vote = cls == CL_IDLE ? 0 : ((__popc(peers) << 4) | cls);
-			const int run_cls = __reduce_max_sync(0xffffffffu, vote) & 15;
-			if (cls != run_cls)
-				continue;
-
-			int wc_stage = 0; // 0: pick the next span end, 1: keep extending the helix
-			switch (ph) {
-			case PH_IDLE:
-				break;
-
-			case PH_WC_RESUME:
-				unmark(L, sm_ds[s].d);
-				unmark(L, sm_ds[s].d3);
-				wc_stage = 1;
-				ph = PH_SPAN;
-				goto do_span;
-
-			case PH_SS_RESUME:
-				unmark(L, sm_ds[s].d);
-				ph = PH_SPAN;
-				goto do_span;
-
-			case PH_PH_RESUME:
-				unmark(L, sm_ds[s].d);
-				unmark(L, sm_ds[s].d3);
-				ph = PH_SPAN;
-				goto do_span;
-
-			case PH_ENTER: {
-				// find_motif, src/find_motif.c:245-287
-				const DevSearch &S = sm_ds[s];
-				const uint32_t zd = L_ZD(L, s);
-				const int z = lo16(zd), dl = hi16(zd);
-				int sd, lsd;
-				if (S.loop) {
-					sd = min(dl, z + S.maxglen - 1);
-					lsd = z + S.minglen - 1;
-				} else
-					sd = lsd = dl;
-				if (S.kind == K_SS) {
-					// find_ss accepts lengths in [minlen, maxlen] only, src/find_motif.c:349
-					sd = min(sd, z + S.maxlen - 1);
-					lsd = max(lsd, z + S.minlen - 1);
-				}
-				L_FR(L, s, 0) = pk16(sd + 1, lsd);
-				if (S.kind == K_WC || S.kind == K_QU) {
-					// no candidate mask yet
-					L_FR(L, s, 5) = 0;
-					L_FR(L, s, 6) = 0;
-				}
-				ph = PH_SPAN;
-			}
-			// fall through
-			case PH_SPAN:
-			do_span: {
-				const DevSearch &S = sm_ds[s];
-				const uint32_t zd = L_ZD(L, s);
-				const int z = lo16(zd), dl = hi16(zd);
-				const uint32_t w0 = L_FR(L, s, 0);
-				int sd = lo16(w0) - 1;
-				const int lsd = hi16(w0);
-
-				if (S.kind == K_SS) {
-					// find_motif's span loop + find_ss (src/find_motif.c:268-280,332-398)
-					// fused: run down the span ends to the next one that is accepted
-					for (;; sd--) {
-						if (sd < lsd) {
-							GM_RETURN();
-							break;
-						}
-						const int len = sd - z + 1;
-						set_cnt(L, S.d, 0, 0);
-						if (S.rx5 >= 0 && !chk_seq5(L, S, z, len))
-							continue;
-						mark(L, S.d, z, len);
-						if (S.next_s >= 0)
-							L_ZD(L, S.next_s) = pk16(sd + 1, dl);
-						if (S.last) {
-							sink(L, A);
-							unmark(L, S.d);
-							continue;
-						}
-						L_FR(L, s, 0) = pk16(sd, lsd);
-						L_FR(L, s, 1) = pk16(0, PH_SS_RESUME);
-						s++;
-						ph = PH_ENTER;
-						break;
-					}
-					break;
-				}
-
-				if (S.kind == K_WC) {
-					// find_motif's span loop + find_wchlx + match_wchlx
-					// (src/find_motif.c:268-280,400-463,975-1112) fused: one trip =
-					// advance to the next helix candidate of this level, or return
-					const int s5 = z;
-					int top = sd, clo = hi16(L_FR(L, s, 4));
-					uint64_t v = (uint64_t)L_FR(L, s, 5) | ((uint64_t)L_FR(L, s, 6) << 32);
-					int s3 = 0, s3lim = 0, hl = 0, mpr = 0, lbpr = 1;
-					if (wc_stage) {
-						const uint32_t w3 = L_FR(L, s, 3);
-						const int f1 = lo16(L_FR(L, s, 1));
-						s3 = hi16(L_FR(L, s, 2));
-						s3lim = lo16(w3);
-						hl = hi16(w3);
-						mpr = f1 & 0xff;
-						lbpr = (f1 >> 8) & 1;
-					}
-					for (;;) {
-						bool cand = false;
-						if (!wc_stage) {
-							// next span end from the candidate mask: `top` is the largest
-							// span end no chunk has covered; bit j of v <-> clo + j
-							while (v == 0) {
-								if (top < lsd)
-									break;
-								clo = max(lsd, top - 63);
-								v = wc_mask(pb, L.sq, strand, sqbase, S.dupi, S.flt, z, clo, top - clo + 1);
-								top = clo - 1;
-							}
-							if (v == 0) {
-								GM_RETURN();
-								break;
-							}
-							const int j = 63 - __clzll((long long)v);
-							v &= ~(1ull << j);
-							s3 = clo + j;
-							int t3 = s3 - z + 1;
-							t3 = (t3 - S.minilen) / 2;
-							t3 = min(t3, S.maxlen);
-							s3lim = s3 - t3 + 1;
-							hl = 0; mpr = 0; lbpr = 1;
-							wc_stage = 1;
-							// the empty helix (minlen = 0) comes first, src/find_motif.c:986-1006
-							cand = S.minlen == 0 && s3 - s5 + 1 <= S.maxilen;
-						}
-						if (!cand) {
-							if (!wx_next(L, S, s5, s3, s3lim, hl, mpr, lbpr)) {
-								wc_stage = 0;
-								continue;
-							}
-							// find_wchlx, src/find_motif.c:441-447
-							if (s3 - s5 - 2 * hl + 1 > S.maxilen)
-								continue;
-						}
-						// descend into the interior with this helix
-						L_FR(L, s, 0) = pk16(top + 1, lsd);
-						L_FR(L, s, 1) = pk16(FR1_LO(mpr, lbpr, 0), PH_WC_RESUME);
-						L_FR(L, s, 2) = pk16(s5, s3);
-						L_FR(L, s, 3) = pk16(s3lim, hl);
-						L_FR(L, s, 4) = pk16(0, clo);
-						L_FR(L, s, 5) = (uint32_t)v;
-						L_FR(L, s, 6) = (uint32_t)(v >> 32);
-						set_cnt(L, S.d, mpr, 0);
-						set_cnt(L, S.d3, mpr, 0);
-						mark(L, S.d, s5, hl);
-						mark(L, S.d3, s3 - hl + 1, hl);
-						if (S.next_s >= 0)
-							L_ZD(L, S.next_s) = pk16(s3 + 1, dl);
-						L_ZD(L, s + 1) = pk16(s5 + hl, s3 - hl);
-						s++;
-						ph = PH_ENTER;
-						break;
-					}
-					break;
-				}
-				if (S.kind == K_WC || S.kind == K_QU) {
-					// span ends come from the candidate mask.  `top` (= sd here) is
-					// the largest span end no chunk has covered yet; a chunk is
-					// [clo, clo + 63] and bit j of v stands for span end clo + j.
-					uint64_t v = (uint64_t)L_FR(L, s, 5) | ((uint64_t)L_FR(L, s, 6) << 32);
-					int clo = hi16(L_FR(L, s, 4));
-					int top = sd;
-					while (v == 0) {
-						if (top < lsd)
-							break;
-						clo = max(lsd, top - 63);
-						v = wc_mask(pb, L.sq, strand, sqbase, S.dupi, S.flt, z, clo, top - clo + 1);
-						top = clo - 1;
-					}
-					if (v == 0) {
-						L_FR(L, s, 0) = pk16(top + 1, lsd);
-						GM_RETURN();
-						break;
-					}
-					const int j = 63 - __clzll((long long)v);
-					v &= ~(1ull << j);
-					sd = clo + j;
-					L_FR(L, s, 5) = (uint32_t)v;
-					L_FR(L, s, 6) = (uint32_t)(v >> 32);
-					L_FR(L, s, 4) = pk16(0, clo);
-					L_FR(L, s, 0) = pk16(top + 1, lsd);
-				} else {
-					if (sd < lsd) {
-						GM_RETURN();
-						break;
-					}
-					L_FR(L, s, 0) = pk16(sd, lsd);
-				}
-				if (S.next_s >= 0)
-					L_ZD(L, S.next_s) = pk16(sd + 1, dl);
-
-				switch (S.kind) {
-				case K_SS: {
-					// find_ss, src/find_motif.c:332-398
-					const int len = sd - z + 1;
-					set_cnt(L, S.d, 0, 0);
-					if (len < S.minlen || len > S.maxlen)
-						break;
-					if (S.rx5 >= 0 && !chk_seq5(L, S, z, len))
-						break;
-					mark(L, S.d, z, len);
-					if (S.last) {
-						sink(L, A);
-						unmark(L, S.d);
-					} else {
-						L_FR(L, s, 1) = pk16(0, PH_SS_RESUME);
-						s++;
-						ph = PH_ENTER;
-					}
-					break;
-				}
-				case K_WC:
-				case K_QU: {
-					// find_wchlx :400-433 / find_4plex :851-892
-					set_cnt(L, S.d, 0, 0);
-					set_cnt(L, S.d3, 0, 0);
-					int i_minl = S.minilen;
-					if (S.kind == K_QU) {
-						const gm_elem_t &e = c_plan.elems[S.d];
-						set_cnt(L, e.mates[0], 0, 0);
-						set_cnt(L, e.mates[1], 0, 0);
-						i_minl = S.minilen + c_plan.elems[e.mates[0]].minilen +
-							c_plan.elems[e.mates[1]].minilen + 2 * S.minlen;
-					}
-					int t3 = sd - z + 1;
-					t3 = (t3 - i_minl) / 2;
-					t3 = min(t3, S.maxlen);
-					const int s3lim = sd - t3 + 1;
-					L_FR(L, s, 2) = pk16(z, sd);
-					L_FR(L, s, 3) = pk16(s3lim, 0);
-					ph = S.minlen == 0 ? PH_WX_BEGIN : PH_WX_FIRST;
-					break;
-				}
-				case K_PK: {
-					// find_pknot + find_pknot5, src/find_motif.c:465-528
-					const gm_elem_t &e = c_plan.elems[S.d];
-					const int *sc = &c_plan.scopes[e.scopes];
-					if (e.scope == 0) {
-						for (int k = 1; k < e.n_scopes; k++) {
-							const int d1 = sc[k];
-							if (c_plan.elems[d1].type == GM_H5) {
-								unmark(L, d1);
-								L_ZD(L, c_plan.elems[d1].searchno) = pk16(z, sd);
-							}
-						}
-					}
-					const int d0 = sc[0], dn = sc[e.n_scopes - 1];
-					const int slen = sd - z + 1;
-					const int p_minl = pk_minlen(L, sm_elmm, d0, S.d - 1);
-					const int p_maxl = pk_maxlen(L, sm_elmm, d0, S.d - 1);
-					const int r_minl = pk_minlen(L, sm_elmm, S.d, dn);
-					const int r_maxl = pk_maxlen(L, sm_elmm, S.d, dn);
-					if (p_maxl + r_maxl < slen)
-						break;
-					const int f_s5 = z + p_minl;
-					const int l_s5 = z + min(p_maxl, slen - r_minl);
-					L_FR(L, s, 4) = pk16(f_s5 - 1, l_s5);
-					ph = PH_PK_S5;
-					break;
-				}
-				case K_PH: {
-					// find_phlx, src/find_motif.c:703-761
-					set_cnt(L, S.d, 0, 0);
-					set_cnt(L, S.d3, 0, 0);
-					const int slen = sd - z + 1;
-					int s5hi = min((slen - S.minilen) / 2, S.maxlen);
-					s5hi = z + s5hi - 1;
-					int ilen = slen - 2 * S.minlen;
-					ilen = min(ilen, S.maxilen);
-					int s5lo = slen - ilen;
-					if (s5lo & 1)
-						s5lo++;
-					s5lo = min(s5lo / 2, S.maxlen);
-					s5lo = z + s5lo - 1;
-					int hlen, n_mpr;
-					if (!match_phlx(L, S, S.d3, z, sd, s5hi, s5lo, &hlen, &n_mpr))
-						break;
-					if (sd - z - 2 * hlen + 1 > S.maxilen)
-						break;
-					set_mpr(L, S.d, n_mpr);
-					set_mpr(L, S.d3, n_mpr);
-					mark(L, S.d, z, hlen);
-					mark(L, S.d3, sd - hlen + 1, hlen);
-					L_ZD(L, s + 1) = pk16(z + hlen, sd - hlen);
-					L_FR(L, s, 1) = pk16(0, PH_PH_RESUME);
-					s++;
-					ph = PH_ENTER;
-					break;
-				}
-				case K_TR: {
-					// find_triplex, src/find_motif.c:763-819
-					const gm_elem_t &e = c_plan.elems[S.d];
-					const int dd1 = e.mates[0], dd2 = e.mates[1];
-					const gm_elem_t &e1 = c_plan.elems[dd1];
-					set_cnt(L, S.d, 0, 0);
-					set_cnt(L, dd1, 0, 0);
-					set_cnt(L, dd2, 0, 0);
-					const int slen = sd - z + 1;
-					int s5hi = min((slen - S.minilen - e1.minilen) / 2, S.maxlen);
-					s5hi = z + s5hi - 1;
-					int i_len = slen - 2 * S.minlen;
-					i_len = min(i_len, S.maxilen + S.minlen + e1.maxilen);
-					int s5lo = slen - i_len;
-					if (s5lo & 1)
-						s5lo++;
-					s5lo = min(s5lo / 2, S.maxlen);
-					s5lo = z + s5lo - 1;
-					int hlen, n_mpr;
-					if (!match_phlx(L, S, dd2, z, sd, s5hi, s5lo, &hlen, &n_mpr))
-						break;
-					if (sd - z - 2 * hlen + 1 > S.maxilen + e1.maxilen + hlen)
-						break;
-					mark(L, S.d, z, hlen);
-					mark(L, dd2, sd - hlen + 1, hlen);
-					L_FR(L, s, 2) = pk16(z, sd);
-					L_FR(L, s, 4) = pk16(sd - e1.minilen - hlen + 1, hlen);
-					ph = PH_TR_S;
-					break;
-				}
-				}
-				break;
-			}
-
-			case PH_WX_BEGIN: {
-				// the empty-helix candidate of match_wchlx, src/find_motif.c:986-1006
-				// (gm_plan_check refuses seq= on a minlen=0 helix, so it is unconditional)
-				const DevSearch &S = sm_ds[s];
-				const uint32_t w2 = L_FR(L, s, 2);
-				const int s5 = lo16(w2), s3 = hi16(w2);
-				L_FR(L, s, 1) = pk16(FR1_LO(0, 1, 0), PH_WX_RESUME);
-				// after this candidate the first pair is tested: hl stays 0
-				if (S.kind == K_WC) {
-					if (s3 - s5 + 1 > S.maxilen) {
-						ph = PH_WX_FIRST;
-						break;
-					}
-					set_mpr(L, S.d, 0);
-					set_mpr(L, S.d3, 0);
-					mark(L, S.d, s5, 0);
-					mark(L, S.d3, s3 + 1, 0);
-					L_ZD(L, s + 1) = pk16(s5, s3);
-					s++;
-					ph = PH_ENTER;
-				} else if (S.kind == K_QU) {
-					mark(L, S.d, s5, 0);
-					mark(L, S.d3, s3 + 1, 0);
-					L_FR(L, s, 7) = pk16(s5 + S.minilen - 1, 0);
-					ph = PH_QU_S1;
-				} else
-					ph = PH_WX_FIRST; // K_PK with minlen 0 is refused by gm_plan_check
-				break;
-			}
-
-			case PH_WX_RESUME: {
-				const DevSearch &S = sm_ds[s];
-				unmark(L, S.d);
-				unmark(L, S.d3);
-				if (hi16(L_FR(L, s, 3)) == 0) {
-					// came back from the empty-helix candidate
-					ph = PH_WX_FIRST;
-					break;
-				}
-				ph = PH_WX_EXT;
-			}
-			// fall through
-			case PH_WX_FIRST:
-			case PH_WX_EXT: {
-				// match_wchlx, src/find_motif.c:1008-1109, one candidate at a time
-				const DevSearch &S = sm_ds[s];
-				const uint32_t w2 = L_FR(L, s, 2), w3 = L_FR(L, s, 3);
-				const int s5 = lo16(w2), s3 = hi16(w2), s3lim = lo16(w3);
-				int hl, mpr, lbpr, chk;
-				if (ph == PH_WX_FIRST) {
-					if (paired(S.duplex, L.sq[s5], L.sq[s3])) {
-						hl = 1; mpr = 0; lbpr = 1;
-					} else if (!(S.ends & GM_5PAIRED)) {
-						hl = 1; mpr = 1; lbpr = 0;
-					} else {
-						ph = S.kind == K_PK ? PH_PK_S3 : PH_SPAN;
-						break;
-					}
-					chk = 1;
-				} else {
-					const int f1 = lo16(L_FR(L, s, 1));
-					hl = hi16(w3);
-					mpr = f1 & 0xff;
-					lbpr = (f1 >> 8) & 1;
-					chk = (f1 >> 9) & 1;
-				}
-				int found = 0;
-				for (;;) {
-					if (chk) {
-						chk = 0;
-						if (hl >= S.minlen &&
-						    !(!lbpr && (S.ends & GM_3PAIRED)) &&
-						    !(S.pfrac && mpr > c_plan.lentab[S.lentab + hl]) &&
-						    !(S.rx5 >= 0 && !rx_match(c_plan.regex[S.rx5], L.sq + s5, hl)) &&
-						    !(S.rx3 >= 0 && !rx_match(c_plan.regex[S.rx3], L.sq + s3 - hl + 1, hl))) {
-							if (S.kind == K_WC) {
-								// find_wchlx, src/find_motif.c:441-447
-								if (s3 - s5 - 2 * hl + 1 <= S.maxilen)
-									found = 1;
-							} else if (S.kind == K_PK) {
-								const int i_minl = hi16(L_FR(L, s, 5));
-								// find_pknot3, src/find_motif.c:609-627
-								if ((s3 - s5 + 1) - 2 * hl < i_minl) {
-									found = -1; // "break": no more for this s3
-									break;
-								}
-								found = 1;
-								const gm_elem_t &e = c_plan.elems[S.d];
-								const int *sc = &c_plan.scopes[e.scopes];
-								if (S.d == sc[1]) {
-									const int d3_h1 = c_plan.elems[sc[0]].mates[0];
-									const int iL_last = m_off(L, d3_h1) - 1;
-									const int iR_last = m_off(L, d3_h1) + m_len(L, d3_h1);
-									int iL_minl = 0, iL_maxl = 0, iR_minl = 0, iR_maxl = 0;
-									if (S.d + 1 <= d3_h1 - 1) {
-										iL_minl = pk_minlen(L, sm_elmm, S.d + 1, d3_h1 - 1);
-										iL_maxl = pk_maxlen(L, sm_elmm, S.d + 1, d3_h1 - 1);
-									}
-									if (d3_h1 + 1 <= S.d3 - 1) {
-										iR_minl = pk_minlen(L, sm_elmm, d3_h1 + 1, S.d3 - 1);
-										iR_maxl = pk_maxlen(L, sm_elmm, d3_h1 + 1, S.d3 - 1);
-									}
-									const int iL = iL_last - (s5 + hl - 1);
-									const int iR = (s3 - hl + 1) - iR_last;
-									if (iL < iL_minl || iL > iL_maxl || iR < iR_minl || iR > iR_maxl)
-										found = 0;
-								}
-							} else
-								found = 1; // K_QU: every helix goes to find_4plex_inner
-							if (found)
-								break;
-						}
-					}
-					if (s3 - hl + 1 < s3lim || hl >= S.maxlen) {
-						found = -1;
-						break;
-					}
-					if (paired(S.duplex, L.sq[s5 + hl], L.sq[s3 - hl]))
-						lbpr = 1;
-					else {
-						if (++mpr > S.mplim) {
-							found = -1;
-							break;
-						}
-						lbpr = 0;
-					}
-					hl++;
-					chk = 1;
-				}
-				if (found < 0) {
-					ph = S.kind == K_PK ? PH_PK_S3 : PH_SPAN;
-					break;
-				}
-				// a candidate: remember where the extension stands
-				L_FR(L, s, 3) = pk16(s3lim, hl);
-				L_FR(L, s, 1) = pk16(FR1_LO(mpr, lbpr, 0), PH_WX_RESUME);
-				mark(L, S.d, s5, hl);
-				mark(L, S.d3, s3 - hl + 1, hl);
-				if (S.kind == K_WC) {
-					set_mpr(L, S.d, mpr);
-					set_mpr(L, S.d3, mpr);
-					L_ZD(L, s + 1) = pk16(s5 + hl, s3 - hl);
-					s++;
-					ph = PH_ENTER;
-				} else if (S.kind == K_PK) {
-					set_mpr(L, S.d, mpr);
-					set_mpr(L, S.d3, mpr);
-					upd_pksearches(L, S.d, s5, s3, hl);
-					s++;
-					ph = PH_ENTER;
-				} else {
-					// find_4plex_inner, src/find_motif.c:937-938
-					L_FR(L, s, 7) = pk16(s5 + hl + S.minilen - 1, 0);
-					ph = PH_QU_S1;
-				}
-				break;
-			}
-
-			case PH_PK_S5: {
-				// find_pknot5 loop + find_pknot3 prologue, src/find_motif.c:523-568
-				const DevSearch &S = sm_ds[s];
-				const uint32_t w4 = L_FR(L, s, 4);
-				const int s5 = lo16(w4) + 1, l_s5 = hi16(w4);
-				if (s5 > l_s5) {
-					ph = PH_SPAN;
-					break;
-				}
-				L_FR(L, s, 4) = pk16(s5, l_s5);
-				const gm_elem_t &e = c_plan.elems[S.d];
-				const int dn = c_plan.scopes[e.scopes + e.n_scopes - 1];
-				const int sd = lo16(L_FR(L, s, 0));
-				const int slen = sd - s5 + 1;
-				const int i_minl = pk_minlen(L, sm_elmm, S.d + 1, S.d3 - 1);
-				const int g_minl = 2 * S.minlen + i_minl;
-				const int s_minl = pk_minlen(L, sm_elmm, S.d3 + 1, dn);
-				const int s_maxl = pk_maxlen(L, sm_elmm, S.d3 + 1, dn);
-				if (g_minl + s_minl > slen)
-					break; // next s5
-				const int f_s3 = sd - s_minl;
-				const int l_s3 = sd - min(slen - g_minl, s_maxl);
-				L_FR(L, s, 2) = pk16(s5, f_s3 + 1);
-				L_FR(L, s, 5) = pk16(l_s3, i_minl);
-				L_FR(L, s, 7) = 0;
-				L_FR(L, s, 8) = 0;
-				L_FR(L, s, 6) = pk16(f_s3, 0); // (largest 3' end not yet covered, chunk low end)
-				ph = PH_PK_S3;
-				break;
-			}
-
-			case PH_PK_S3: {
-				// find_pknot3 loop over the 3' end, src/find_motif.c:600-606,
-				// through the same candidate mask as the proper helices
-				const DevSearch &S = sm_ds[s];
-				const uint32_t w2 = L_FR(L, s, 2), w5 = L_FR(L, s, 5), w6 = L_FR(L, s, 6);
-				const int s5 = lo16(w2);
-				const int l_s3 = lo16(w5), i_minl = hi16(w5);
-				int top = lo16(w6), clo = hi16(w6);
-				uint64_t v = (uint64_t)L_FR(L, s, 7) | ((uint64_t)L_FR(L, s, 8) << 32);
-				while (v == 0) {
-					if (top < l_s3)
-						break;
-					clo = max(l_s3, top - 63);
-					v = wc_mask(pb, L.sq, strand, sqbase, S.dupi, S.flt, s5, clo, top - clo + 1);
-					top = clo - 1;
-				}
-				if (v == 0) {
-					ph = PH_PK_S5;
-					break;
-				}
-				const int j = 63 - __clzll((long long)v);
-				v &= ~(1ull << j);
-				const int s3 = clo + j;
-				L_FR(L, s, 7) = (uint32_t)v;
-				L_FR(L, s, 8) = (uint32_t)(v >> 32);
-				L_FR(L, s, 6) = pk16(top, clo);
-				L_FR(L, s, 2) = pk16(s5, s3);
-				int t3 = s3 - s5 + 1;
-				t3 = (t3 - i_minl) / 2;
-				t3 = min(t3, S.maxlen);
-				L_FR(L, s, 3) = pk16(s3 - t3 + 1, 0);
-				ph = PH_WX_FIRST;
-				break;
-			}
-
-			case PH_TR_RESUME:
-				unmark(L, c_plan.elems[sm_ds[s].d].mates[0]);
-				ph = PH_TR_S;
-			// fall through
-			case PH_TR_S: {
-				// find_triplex loop over the t2 end, src/find_motif.c:821-845
-				const DevSearch &S = sm_ds[s];
-				const gm_elem_t &e = c_plan.elems[S.d];
-				const int dd1 = e.mates[0], dd2 = e.mates[1];
-				const gm_elem_t &e1 = c_plan.elems[dd1];
-				const uint32_t w4 = L_FR(L, s, 4), w2 = L_FR(L, s, 2);
-				const int sp = lo16(w4) - 1, hlen = hi16(w4);
-				const int z = lo16(w2), sd = hi16(w2);
-				if (sp < z + 2 * hlen + S.minilen - 1) {
-					unmark(L, S.d);
-					unmark(L, dd2);
-					ph = PH_SPAN;
-					break;
-				}
-				L_FR(L, s, 4) = pk16(sp, hlen);
-				int n_mpr;
-				if (!match_triplex(L, S, dd1, z, sp, sd, hlen, &n_mpr))
-					break;
-				if (sp - 2 * hlen - z + 1 > S.maxilen)
-					break;
-				if (sd - hlen - sp > e1.maxilen)
-					break;
-				set_mpr(L, S.d, n_mpr);
-				set_mpr(L, dd1, n_mpr);
-				set_mpr(L, dd2, n_mpr);
-				mark(L, dd1, sp - hlen + 1, hlen);
-				L_ZD(L, s + 1) = pk16(z + hlen, sp - hlen);
-				L_ZD(L, c_plan.elems[e1.inner].searchno) = pk16(sp + 1, sd - hlen);
-				L_FR(L, s, 1) = pk16(0, PH_TR_RESUME);
-				s++;
-				ph = PH_ENTER;
-				break;
-			}
-
-			case PH_QU_S1: {
-				// find_4plex_inner outer loop, src/find_motif.c:937-939
-				const DevSearch &S = sm_ds[s];
-				const gm_elem_t &e = c_plan.elems[S.d];
-				const int i2_minl = c_plan.elems[e.mates[0]].minilen;
-				const int i3_minl = c_plan.elems[e.mates[1]].minilen;
-				const int s3 = hi16(L_FR(L, s, 2)), hl = hi16(L_FR(L, s, 3));
-				const int s1 = lo16(L_FR(L, s, 7)) + 1;
-				if (s1 > s3 - 3 * hl - i3_minl - i2_minl) {
-					// this q1/q4 helix is done: back to the extension
-					unmark(L, S.d);
-					unmark(L, S.d3);
-					ph = hl == 0 ? PH_WX_FIRST : PH_WX_EXT;
-					break;
-				}
-				L_FR(L, s, 7) = pk16(s1, s3 - hl - i3_minl + 1);
-				ph = PH_QU_S2;
-				break;
-			}
-
-			case PH_QU_RESUME: {
-				const gm_elem_t &e = c_plan.elems[sm_ds[s].d];
-				unmark(L, e.mates[0]);
-				unmark(L, e.mates[1]);
-				ph = PH_QU_S2;
-			}
-			// fall through
-			case PH_QU_S2: {
-				// find_4plex_inner inner loop, src/find_motif.c:940-969
-				const DevSearch &S = sm_ds[s];
-				const gm_elem_t &e = c_plan.elems[S.d];
-				const int dd1 = e.mates[0], dd2 = e.mates[1];
-				const gm_elem_t &e1 = c_plan.elems[dd1], &e2 = c_plan.elems[dd2];
-				const uint32_t w2 = L_FR(L, s, 2), w7 = L_FR(L, s, 7);
-				const int z = lo16(w2), s3 = hi16(w2), hl = hi16(L_FR(L, s, 3));
-				const int s1 = lo16(w7), s2 = hi16(w7) - 1;
-				if (s2 < s1 + 2 * hl + e1.minilen) {
-					ph = PH_QU_S1;
-					break;
-				}
-				L_FR(L, s, 7) = pk16(s1, s2);
-				int n_mpr;
-				if (!match_4plex(L, dd1, dd2, z, s1, s2, s3, hl, &n_mpr))
-					break;
-				if (s1 - z - hl + 1 > S.maxilen)
-					break;
-				if (s2 - s1 - 2 * hl + 1 > e1.maxilen)
-					break;
-				if (s3 - s2 - hl + 1 > e2.maxilen)
-					break;
-				set_mpr(L, S.d, n_mpr);
-				set_mpr(L, dd1, n_mpr);
-				set_mpr(L, dd2, n_mpr);
-				set_mpr(L, S.d3, n_mpr);
-				mark(L, dd1, s1, hl);
-				mark(L, dd2, s2 - hl + 1, hl);
-				L_ZD(L, s + 1) = pk16(z + hl, s1 - 1);
-				L_ZD(L, c_plan.elems[e1.inner].searchno) = pk16(s1 + hl, s2 - hl);
-				L_ZD(L, c_plan.elems[e2.inner].searchno) = pk16(s2 + 1, s3 - hl);
-				L_FR(L, s, 1) = pk16(lo16(L_FR(L, s, 1)), PH_QU_RESUME);
-				s++;
-				ph = PH_ENTER;
-				break;
-			}
-
-			}
+#define GM_MASK(S, z, clo, n) wc_mask(pb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n))
+#include "gm_machine_body.inc"
+#undef GM_MASK
 		}
 		__syncthreads(); // everyone is done with this tile's shared memory
 	}
@@ -1097,6 +497,195 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		my_starts += __shfl_down_sync(0xffffffffu, my_starts, o);
 	if (lane == 0 && my_starts)
 		atomicAdd(A.start_count, my_starts);
+}
+
+
+// First-pair scan used where no pair bitsets exist (gm_dfs_kernel): span ends
+// in [lo, lo+n) whose outermost pair can form -- what match_wchlx tests first
+// (src/find_motif.c:1010-1021).  A superset filter like wc_mask.
+__device__ __forceinline__ uint64_t wc_mask_scan(const Lane &L, const DevSearch &S, int z, int lo, int n)
+{
+	const uint64_t ones = n >= 64 ? ~0ull : ((1ull << n) - 1);
+	if (!((S.flt >> 16) & 1) || S.minlen == 0)
+		return ones;
+	const unsigned row = S.duplex >> (bcode_of(L.sq[z]) * 5);
+	uint64_t v = 0;
+	for (int j = 0; j < n; j++)
+		v |= (uint64_t)((row >> bcode_of(L.sq[lo + j])) & 1u) << j;
+	return v;
+}
+
+struct DfsSmem {
+	int dummy[16];
+};
+
+// The worklist consumer of the split path: lanes take prefilter survivors from
+// the global worklist (32 at a time per warp), the warp cooperatively builds
+// each new lane's private window (one byte per nucleotide of the searched
+// strand, reverse complement included) straight from the packed database, and
+// the lanes run the same machine as the tile kernel.
+__global__ void gm_dfs_kernel(const ScanArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	const int tid = threadIdx.x, nt = blockDim.x;
+	const int lane = tid & 31, warp = tid >> 5;
+	const int NS = c_par.n_searches, ND = c_par.n_descr;
+	const int W = c_par.w_winsize;
+	const int Lc = c_par.halo - W;            // context nucleotides kept on each side
+	const int wstride = c_par.win_stride;     // bytes per lane window (odd number of words)
+	const int Wtot = W + 2 * Lc;
+
+	uint8_t *p = smem_raw;
+	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
+	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
+	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
+	uint32_t *sm_ent = reinterpret_cast<uint32_t *>(p);        p += (size_t)nt * GM_WL_WORDS * 4;
+	uint8_t *sm_wst = p;                                       p += (size_t)nt * c_par.win_stage;
+	uint8_t *sm_win = p;                                       p += (size_t)nt * wstride;
+	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
+
+	for (int i = tid; i < NS * (int)(sizeof(DevSearch) / 4); i += nt)
+		reinterpret_cast<uint32_t *>(sm_ds)[i] = reinterpret_cast<const uint32_t *>(c_ds)[i];
+	for (int i = tid; i < c_plan.n_pairsets * (int)(sizeof(gm_pairset_t) / 4); i += nt)
+		reinterpret_cast<uint32_t *>(sm_ps)[i] = reinterpret_cast<const uint32_t *>(c_plan.pairsets)[i];
+	for (int i = tid; i < ND; i += nt)
+		sm_elmm[i] = pk16(c_plan.elems[i].minlen, c_plan.elems[i].maxlen);
+
+	Lane L;
+	L.st = sm_state + tid;
+	L.nt = nt;
+	L.ds = sm_ds;
+	L.ps = sm_ps;
+	L.NS = NS;
+	L.ND = ND;
+	L.el_base = NS + c_par.frame_words;
+	uint8_t *mywin = sm_win + (size_t)tid * wstride;
+	L.sq = mywin + Lc;
+	L.szero = L.slen = L.comp = 0;
+	L.rec = 0;
+	L.seq = 0;
+	for (int d = 0; d < ND; d++) {
+		unmark(L, d);
+		set_cnt(L, d, GM_UNDEF, GM_UNDEF);
+	}
+	uint32_t *went = sm_ent + (size_t)warp * 32 * GM_WL_WORDS;
+	const int wst = c_par.win_stage;          // packed bytes staged per worklist entry
+	uint8_t *wstage = sm_wst + (size_t)warp * 32 * wst;
+	__syncthreads();
+
+	const unsigned long long wl_n = min(*A.wl_count, A.wl_cap);
+	int s = 0, ph = PH_IDLE;
+	bool exhausted = false;
+	int bavail = 0, bnext = 0; // entries of the current batch not yet handed out (warp-uniform)
+
+	for (;;) {
+		const unsigned idle = __ballot_sync(0xffffffffu, ph == PH_IDLE);
+		if (idle) {
+			if (bavail == 0 && !exhausted) {
+				// next batch of 32 worklist entries, staged in shared memory
+				unsigned long long base = 0;
+				if (lane == 0)
+					base = atomicAdd(A.wl_head, 32ull);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (base >= wl_n)
+					exhausted = true;
+				else {
+					bavail = (int)min((unsigned long long)32, wl_n - base);
+					bnext = 0;
+					if (lane < bavail) {
+						const uint4 *e = reinterpret_cast<const uint4 *>(A.wl + (base + lane) * GM_WL_WORDS);
+						uint4 *d = reinterpret_cast<uint4 *>(went + lane * GM_WL_WORDS);
+						const uint4 e0 = e[0], e1v = e[1];
+						d[0] = e0;
+						d[1] = e1v;
+						// stage the packed bytes under this entry's window now, all 32
+						// entries of the batch at once (one memory latency per batch)
+						const int ecomp = (int)(e0.y >> 31), eslen = (int)e0.w, eszero = (int)e1v.x;
+						const int64_t roff = A.rec_off[e0.z];
+						int c0 = max(eszero - Lc, 0), c1 = min(eszero - Lc + Wtot, eslen); // strand coords [c0, c1)
+						if (c1 < c0)
+							c1 = c0;
+						const int64_t gs = roff + (ecomp ? eslen - c1 : c0); // first forward nucleotide
+						const int64_t b16 = (gs >> 1) & ~(int64_t)15;
+						d[1].w = (uint32_t)((gs >> 1) - b16) | ((uint32_t)(gs & 1) << 8); // byte/nibble of gs in the stage
+						const uint4 *src = reinterpret_cast<const uint4 *>(A.packed + b16);
+						uint4 *dst = reinterpret_cast<uint4 *>(wstage + (size_t)lane * wst);
+						for (int k = 0; k < (wst >> 4); k++)
+							dst[k] = src[k];
+					}
+					__syncwarp();
+				}
+			}
+			const int rank = __popc(idle & ((1u << lane) - 1));
+			const bool take = ph == PH_IDLE && rank < bavail;
+			const unsigned tm = __ballot_sync(0xffffffffu, take);
+			uint32_t e1 = 0, v0lo = 0, v0hi = 0;
+			if (take) {
+				const uint32_t *e = went + (bnext + rank) * GM_WL_WORDS;
+				e1 = e[1];
+				L.rec = e[2];
+				L.slen = (int)e[3];
+				L.szero = (int)e[4];
+				L.comp = (int)(e1 >> 31);
+				L.seq = 0;
+				v0lo = e[5];
+				v0hi = e[6];
+			}
+			// build the windows of the lanes that took a start, one lane at a time,
+			// all 32 lanes copying
+			const int myslot = bnext + rank; // batch slot of the entry this lane took
+			for (unsigned m = tm; m; m &= m - 1) {
+				const int j = __ffs(m) - 1;
+				const int jcomp = __shfl_sync(0xffffffffu, L.comp, j);
+				const int jslen = __shfl_sync(0xffffffffu, L.slen, j);
+				const int jszero = __shfl_sync(0xffffffffu, L.szero, j);
+				const int jslot = __shfl_sync(0xffffffffu, myslot, j);
+				const uint32_t where = went[jslot * GM_WL_WORDS + 7];
+				const int nib0 = (int)(where & 0xff) * 2 + (int)((where >> 8) & 1); // nibble index of gs
+				const uint8_t *stg = wstage + (size_t)jslot * wst;
+				uint8_t *win = sm_win + (size_t)((warp << 5) + j) * wstride;
+				const int c0 = max(jszero - Lc, 0), c1 = max(min(jszero - Lc + Wtot, jslen), c0);
+				for (int i = lane; i < Wtot; i += 32) {
+					const int c = jszero - Lc + i; // strand coordinate
+					uint8_t v = (uint8_t)(4 << 4);
+					if (c >= c0 && c < c1) {
+						// forward nucleotide gs + k lies k nibbles into the stage
+						const int k = nib0 + (jcomp ? c1 - 1 - c : c - c0);
+						const unsigned byte = stg[k >> 1];
+						v = expand_code((byte >> ((k & 1) * 4)) & 15);
+						if (jcomp)
+							v = complement_byte(v);
+					}
+					win[i] = v;
+				}
+			}
+			__syncwarp();
+			if (take) {
+				const DevSearch &S0 = sm_ds[0];
+				const int dl = min(W, L.slen - L.szero) - 1;
+				L_ZD(L, 0) = pk16(0, dl);
+				s = 0;
+				ph = PH_ENTER;
+				if ((e1 >> 30) & 1) {
+					// the prefilter already computed search 0's candidate mask
+					const int lsd = S0.minglen - 1;
+					L_FR(L, 0, 0) = pk16(lsd, lsd);   // nothing left above the chunk
+					L_FR(L, 0, 4) = pk16(0, lsd);
+					L_FR(L, 0, 5) = v0lo;
+					L_FR(L, 0, 6) = v0hi;
+					ph = PH_SPAN;
+				}
+			}
+			const int took = __popc(tm);
+			bavail -= took;
+			bnext += took;
+			if (exhausted && bavail == 0 && __all_sync(0xffffffffu, ph == PH_IDLE))
+				break;
+		}
+#define GM_MASK(S, z, clo, n) wc_mask_scan(L, (S), (z), (clo), (n))
+#include "gm_machine_body.inc"
+#undef GM_MASK
+	}
 }
 
 } // namespace gm

@@ -60,6 +60,8 @@ struct DevParams {
 	int tile;               // starts per tile
 	int words_per_lane;
 	int frame_words;        // sum of all frames
+	int win_stride;         // split path: bytes of one lane window
+	int win_stage;          // split path: packed bytes staged per worklist entry (multiple of 16)
 	int n_dups;             // distinct duplex tables with pair bitsets
 	unsigned dups[GM_MAX_DUPS];
 };

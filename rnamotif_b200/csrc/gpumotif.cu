@@ -66,6 +66,13 @@ struct gm_ctx {
 	int stride_words;
 	int threads, blocks;
 	size_t smem_bytes;
+	// split path (prefilter kernel -> worklist -> dfs kernel)
+	bool use_split;
+	int a_threads, a_blocks, b_threads, b_blocks;
+	size_t a_smem, b_smem;
+	uint32_t *d_wl;
+	size_t wl_cap;        // entries
+	int64_t seg_nt;       // nucleotides per prefilter/dfs launch pair
 	std::vector<uint32_t> hits;    // sorted, host
 	size_t n_hits;
 	gm_scan_stats_t stats;
@@ -302,7 +309,7 @@ extern "C" int gm_plan_check(const gm_plan_t *plan)
 
 // -------------------------------------------------------------- context
 
-static size_t smem_need(const gm_ctx *c, int threads, int tile)
+static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state = true)
 {
 	const int Lb = (tile + 2 * c->par.halo + 15) & ~15;
 	size_t n = 64;
@@ -314,6 +321,20 @@ static size_t smem_need(const gm_ctx *c, int threads, int tile)
 	n += (c->par.n_descr * 4 + 15) & ~15;
 	n += (GM_REC_CACHE + 1) * 8;
 	n += (size_t)(threads >> 5) * GM_QCAP * 2;
+	if (with_state)
+		n += (size_t)c->par.words_per_lane * threads * 4;
+	return n;
+}
+
+static size_t dfs_smem_need(const gm_ctx *c, int threads)
+{
+	size_t n = 0;
+	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
+	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
+	n += (c->par.n_descr * 4 + 15) & ~15;
+	n += (size_t)threads * GM_WL_WORDS * 4;
+	n += (size_t)threads * c->par.win_stage;
+	n += (size_t)threads * c->par.win_stride;
 	n += (size_t)c->par.words_per_lane * threads * 4;
 	return n;
 }
@@ -338,13 +359,69 @@ static int configure_launch(gm_ctx *c, int tile)
 	c->threads = best_t;
 	c->par.tile = tile;
 	c->smem_bytes = smem_need(c, best_t, tile);
-	CU(cudaFuncSetAttribute(gm_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+	CU(cudaFuncSetAttribute(gm_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
 	int per_sm = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gm_search_kernel, c->threads, c->smem_bytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gm_search_kernel<0>, c->threads, c->smem_bytes));
 	if (per_sm < 1)
 		return fail("search kernel does not fit on an SM (threads %d, smem %zu)", c->threads, c->smem_bytes);
 	c->blocks = per_sm * c->n_sm;
+
+	// split path: the worklist kernels.  Eligible when search 0 has a prefilter
+	// worth a pass of its own and a lane window fits comfortably in shared memory.
+	const DevSearch &S0 = c->ds[0];
+	const int wtot = c->par.halo * 2 - c->par.w_winsize;
+	int words = (wtot + 3) / 4;
+	if (!(words & 1))
+		words++;
+	c->par.win_stride = words * 4;
+	c->par.win_stage = (((wtot + 1) / 2 + 1 + 15 + 15) & ~15);
+	bool eligible = wtot <= 512 &&
+		((S0.dupi >= 0 && (S0.flt & 0xff) > 0) ||
+		 (S0.rx5 >= 0 && S0.mm5 == 0 && !c->plan.regex[S0.rx5].eol));
+	// The fused kernel is the default: on the measured configurations it is the
+	// faster of the two (profiles/README.md).  GPUMOTIF_PATH=split selects the
+	// worklist pair, =fused forces the single kernel.
+	const char *force = getenv("GPUMOTIF_PATH");
+	if (force == NULL || strcmp(force, "split") != 0)
+		eligible = false;
+	else if (wtot <= 512)
+		eligible = true;
+	c->use_split = false;
+	if (eligible) {
+		c->a_threads = 256;
+		c->a_smem = smem_need(c, c->a_threads, tile, false);
+		int best_w = 0;
+		c->b_threads = 0;
+		for (int t = 64; t <= 256; t <<= 1) {
+			size_t need = dfs_smem_need(c, t);
+			if (need > smem_sm)
+				continue;
+			int n = 0;
+			if (cudaFuncSetAttribute(gm_dfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
+			    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gm_dfs_kernel, t, need) != cudaSuccess)
+				continue;
+			if (n * t > best_w) {
+				best_w = n * t;
+				c->b_threads = t;
+				c->b_smem = need;
+				c->b_blocks = n * c->n_sm;
+			}
+		}
+		cudaGetLastError();
+		int na = 0;
+		if (c->b_threads > 0 && c->a_smem <= smem_sm &&
+		    cudaFuncSetAttribute(gm_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
+		    cudaFuncSetAttribute(gm_dfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->b_smem) == cudaSuccess &&
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, gm_search_kernel<1>, c->a_threads, c->a_smem) == cudaSuccess &&
+		    na >= 1) {
+			c->a_blocks = na * c->n_sm;
+			c->use_split = true;
+		}
+		cudaGetLastError();
+	}
 	CU(cudaMemcpyToSymbolAsync(c_par, &c->par, sizeof c->par, 0, cudaMemcpyHostToDevice, c->stream));
+	if (c->device < 64 && g_const_owner[c->device] != c)
+		g_const_owner[c->device] = NULL; // force a full re-bind of the __constant__ plan at the next launch
 	return 0;
 }
 
@@ -359,6 +436,10 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->d_rec_off = NULL;
 	c->d_counters = NULL;
 	c->d_hits = NULL;
+	c->d_wl = NULL;
+	c->wl_cap = 0;
+	c->seg_nt = (int64_t)16 << 20;
+	c->use_split = false;
 	c->chars_cap = c->packed_cap = c->rec_cap = 0;
 	c->total_nt = 0;
 	c->n_hits = 0;
@@ -402,7 +483,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	}
 	for (int i = 0; i < 6; i++)
 		cudaEventCreate(&c->ev[i]);
-	if (cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+	if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
 		gm_ctx_destroy(c);
 		return fail("cudaMalloc(counters) failed");
 	}
@@ -435,6 +516,7 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 	cudaFree(c->d_rec_off);
 	cudaFree(c->d_counters);
 	cudaFree(c->d_hits);
+	cudaFree(c->d_wl);
 	for (int i = 0; i < 6; i++)
 		if (c->ev[i])
 			cudaEventDestroy(c->ev[i]);
@@ -505,7 +587,7 @@ static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
 static int pack_on_device(gm_ctx *c, const uint8_t *d_chars)
 {
 	const int64_t n = c->total_nt;
-	const size_t pbytes = (size_t)(((n + 15) / 16) * 8) + 64;
+	const size_t pbytes = (size_t)(((n + 15) / 16) * 8) + 1024; // slack: kernels read whole 16-byte groups past the end
 	if (ensure((void **)&c->d_packed, &c->packed_cap, pbytes))
 		return -1;
 	CU(cudaEventRecord(c->ev[1], c->stream));
@@ -593,7 +675,7 @@ static int launch(gm_ctx *c)
 	if (c->d_hits == NULL) {
 		CU(cudaMalloc(&c->d_hits, c->hit_cap * (size_t)c->stride_words * 4));
 	}
-	CU(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+	CU(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
 	ScanArgs A;
 	A.packed = c->d_packed;
 	A.total_nt = c->total_nt;
@@ -609,12 +691,42 @@ static int launch(gm_ctx *c)
 	A.hits = c->d_hits;
 	A.hit_cap = c->hit_cap;
 	A.stride_words = c->stride_words;
+	A.wl = NULL;
+	A.wl_count = c->d_counters + 3;
+	A.wl_head = c->d_counters + 4;
+	A.wl_cap = 0;
 	CU(cudaEventRecord(c->ev[3], c->stream));
-	if (A.n_tiles > 0) {
+	if (A.n_tiles > 0 && !c->use_split) {
 		int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
-		gm_search_kernel<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+		gm_search_kernel<0><<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 		CU(cudaGetLastError());
 		c->stats.n_launches++;
+	} else if (A.n_tiles > 0) {
+		// split path, one (prefilter, dfs) launch pair per segment of the range
+		const int64_t seg = std::min<int64_t>(c->seg_nt, c->p_end - c->p_begin);
+		const size_t need = (size_t)seg * c->p_strands;
+		if (c->d_wl == NULL || c->wl_cap < need) {
+			cudaFree(c->d_wl);
+			c->d_wl = NULL;
+			CU(cudaMalloc(&c->d_wl, need * GM_WL_WORDS * 4));
+			c->wl_cap = need;
+		}
+		A.wl = c->d_wl;
+		A.wl_cap = c->wl_cap;
+		for (int64_t g0 = c->p_begin; g0 < c->p_end; g0 += seg) {
+			A.g_begin = g0;
+			A.g_end = std::min<int64_t>(g0 + seg, c->p_end);
+			A.n_tiles = (A.g_end - A.g_begin + c->par.tile - 1) / c->par.tile;
+			// tile counter, worklist count and head restart for every segment
+			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
+			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
+			int ablocks = (int)std::min<int64_t>(c->a_blocks, A.n_tiles);
+			gm_search_kernel<1><<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
+			CU(cudaGetLastError());
+			gm_dfs_kernel<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
+			CU(cudaGetLastError());
+			c->stats.n_launches += 2;
+		}
 	}
 	CU(cudaEventRecord(c->ev[4], c->stream));
 	return 0;
