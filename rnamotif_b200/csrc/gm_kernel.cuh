@@ -22,7 +22,7 @@ __constant__ gm_plan_t c_plan;
 __constant__ DevSearch c_ds[GM_MAX_DESCR];
 __constant__ DevParams c_par;
 
-#define GM_REC_CACHE 512
+#define GM_REC_CACHE 62
 
 struct ScanArgs {
 	const uint8_t *packed;      // 4-bit codes, nucleotide g in byte g>>1, nibble g&1
@@ -138,7 +138,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // -------------------------------------------------------------- the sink
 
 // element type covering window-relative position p, or -1 (fm_window == UNDEF)
-__device__ int wtype(const Lane &L, int p)
+__device__ __noinline__ int wtype(const Lane &L, int p)
 {
 	for (int d = 0; d < L.ND; d++) {
 		uint32_t w = L_EL(L, d);
@@ -156,7 +156,7 @@ __device__ __forceinline__ bool is_ss(const Lane &L, int p, bool undef_is_ss)
 
 // chk_motif + chk_wchlx/chk_triplex/chk_4plex, src/find_motif.c:1406-1718
 // (chk_phlx never rejects: every path returns TRUE, :1531,1550,1554)
-__device__ bool sink_strict(const Lane &L)
+__device__ __noinline__ bool sink_strict(const Lane &L)
 {
 	for (int d = 0; d < L.ND; d++) {
 		const gm_elem_t &e = c_plan.elems[d];
@@ -222,7 +222,7 @@ __device__ bool sink_strict(const Lane &L)
 }
 
 // set_context, src/find_motif.c:1720-1756; results in absolute coordinates
-__device__ bool sink_context(const Lane &L, int ctx[4])
+__device__ __noinline__ bool sink_context(const Lane &L, int ctx[4])
 {
 	ctx[0] = ctx[1] = ctx[2] = ctx[3] = -1;
 	if (c_plan.lctx.present) {
@@ -259,7 +259,7 @@ __device__ bool sink_context(const Lane &L, int ctx[4])
 }
 
 // chk_sites / chk_1_site, src/find_motif.c:1758-1808
-__device__ bool sink_sites(const Lane &L)
+__device__ __noinline__ bool sink_sites(const Lane &L)
 {
 	for (int s = 0; s < c_plan.n_sites; s++) {
 		const gm_site_t &si = c_plan.sites[s];
@@ -293,7 +293,7 @@ __device__ bool sink_sites(const Lane &L)
 }
 
 // the hit sink up to RM_score, src/find_motif.c:362-372
-__device__ void sink(Lane &L, const ScanArgs &A)
+__device__ __noinline__ void sink(Lane &L, const ScanArgs &A)
 {
 	int ctx[4];
 	if (c_par.strict_helices && !sink_strict(L))
@@ -316,25 +316,39 @@ __device__ void sink(Lane &L, const ScanArgs &A)
 	h[6] = (uint32_t)ctx[2];
 	h[7] = (uint32_t)ctx[3];
 	for (int d = 0; d < L.ND; d++) {
-		uint32_t el = L_EL(L, d), em = L_EM(L, d);
+		const uint32_t el = L_EL(L, d);
+		int mpr, mm;
+		if (c_par.lite) {
+			// counts live in the frames: a helix head keeps its mispairs, an ss its mismatches
+			const int f1 = lo16(L_FR(L, c_par.elsrc[d], 1));
+			if (c_plan.elems[d].type == GM_SS) {
+				mpr = 0;
+				mm = f1;
+			} else {
+				mpr = f1 & 0xff;
+				mm = 0;
+			}
+		} else {
+			const uint32_t em = L_EM(L, d);
+			mpr = lo16(em);
+			mm = hi16(em);
+		}
 		h[8 + 2 * d] = (uint32_t)(L.szero + lo16(el));
-		h[9 + 2 * d] = (uint32_t)(hi16(el) & 0xffff) | ((uint32_t)(lo16(em) & 0xff) << 16) |
-			((uint32_t)(hi16(em) & 0xff) << 24);
+		h[9 + 2 * d] = (uint32_t)(hi16(el) & 0xffff) | ((uint32_t)(mpr & 0xff) << 16) |
+			((uint32_t)(mm & 0xff) << 24);
 	}
 }
 
 // ------------------------------------------------------------ match helpers
 
-__device__ __forceinline__ int chk_seq5(Lane &L, const DevSearch &S, int off, int len)
+__device__ __forceinline__ int chk_seq5(Lane &L, const DevSearch &S, int off, int len, int &n_mm)
 {
-	// chk_seq on the head element, src/find_motif.c:1810-1824
+	// chk_seq on the head element, src/find_motif.c:1810-1824; n_mm is what it
+	// leaves in s_n_mismatches
 	const gm_regex_t &rx = c_plan.regex[S.rx5];
-	if (S.mm5 > 0) {
-		int n_mm;
-		int ok = rx_match_mm(rx, L.sq + off, len, S.mm5, &n_mm);
-		L_EM(L, S.d) = pk16(lo16(L_EM(L, S.d)), n_mm);
-		return ok;
-	}
+	n_mm = 0;
+	if (S.mm5 > 0)
+		return rx_match_mm(rx, L.sq + off, len, S.mm5, &n_mm);
 	return rx_match(rx, L.sq + off, len);
 }
 
@@ -379,7 +393,7 @@ __device__ __forceinline__ bool wx_next(const Lane &L, const DevSearch &S, int s
 }
 
 // find_minlen / find_maxlen, src/find_motif.c:642-665
-__device__ int pk_minlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
+__device__ __noinline__ int pk_minlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
 {
 	int v = 0;
 	for (int d = fd; d <= ld; d++) {
@@ -388,7 +402,7 @@ __device__ int pk_minlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
 	}
 	return v;
 }
-__device__ int pk_maxlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
+__device__ __noinline__ int pk_maxlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
 {
 	int v = 0;
 	for (int d = fd; d <= ld; d++) {
@@ -399,7 +413,7 @@ __device__ int pk_maxlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
 }
 
 // match_phlx, src/find_motif.c:1114-1181
-__device__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int s5, int s3, int s5hi, int s5lo,
+__device__ __noinline__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int s5, int s3, int s5hi, int s5lo,
 	int *hlen, int *n_mpr)
 {
 	const gm_elem_t &e3 = c_plan.elems[d3];
@@ -440,7 +454,7 @@ __device__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int s5, int s3, 
 }
 
 // match_triplex, src/find_motif.c:1183-1232
-__device__ bool match_triplex(Lane &L, const DevSearch &S, int dd1, int s1, int s2, int s3, int tlen, int *n_mpr)
+__device__ __noinline__ bool match_triplex(Lane &L, const DevSearch &S, int dd1, int s1, int s2, int s3, int tlen, int *n_mpr)
 {
 	const gm_elem_t &e = c_plan.elems[S.d];
 	const gm_elem_t &e1 = c_plan.elems[dd1];
@@ -471,7 +485,7 @@ __device__ bool match_triplex(Lane &L, const DevSearch &S, int dd1, int s1, int 
 
 // match_4plex, src/find_motif.c:1234-1289: parameters come from q2 (stp1);
 // the loop header resets the mispair count (:1260)
-__device__ bool match_4plex(Lane &L, int dd1, int dd2, int s1, int s2, int s3, int s4, int qlen, int *n_mpr)
+__device__ __noinline__ bool match_4plex(Lane &L, int dd1, int dd2, int s1, int s2, int s3, int s4, int qlen, int *n_mpr)
 {
 	const gm_elem_t &e1 = c_plan.elems[dd1];
 	const gm_elem_t &e2 = c_plan.elems[dd2];
@@ -504,7 +518,7 @@ __device__ bool match_4plex(Lane &L, int dd1, int dd2, int s1, int s2, int s3, i
 }
 
 // upd_pksearches, src/find_motif.c:667-701
-__device__ void upd_pksearches(Lane &L, int d, int h5, int h3, int hlen)
+__device__ __noinline__ void upd_pksearches(Lane &L, int d, int h5, int h3, int hlen)
 {
 	const gm_elem_t &e = c_plan.elems[d];
 	const int d3 = e.mates[0];

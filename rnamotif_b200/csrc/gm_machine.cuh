@@ -76,13 +76,11 @@ enum {
 
 #define GM_QCAP 128 // per-warp queue of start items (power of two)
 
-struct Smem {
+// per-warp tile bookkeeping (each warp owns its tile: buffers, mbarrier, queue)
+struct WarpTile {
 	uint64_t bar;
-	int work;          // next chunk of start items of the current tile
 	int r_lo;          // first record intersecting the tile
 	int one_rec;       // the tile lies inside a single record
-	int pad;
-	int64_t tile;      // current tile index (broadcast)
 };
 
 __device__ __forceinline__ uint8_t expand_code(unsigned c)
@@ -149,12 +147,22 @@ __device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, i
 	return (budget == 0 ? a0 : budget == 1 ? a1 : a2) & ones;
 }
 
-// MODE 0: fused -- prefilter and machine in one kernel, lanes refilled from a
-//         per-warp queue, one tile at a time (works for every plan).
+// MODE 0: fused -- prefilter and machine in one kernel (works for every plan).
 // MODE 1: prefilter only -- survivors are appended to a global worklist that
-//         gm_dfs_kernel consumes (the split path: no tile barrier ever waits
-//         for a long enumeration, and the worklist rebalances the starts).
-template <int MODE>
+//         gm_dfs_kernel consumes (the split path).
+//
+// Every warp works on its own: it pulls tiles from the global counter, stages
+// them into one of ITS TWO tile buffers with its own TMA bulk copy + mbarrier,
+// and keeps its lanes fed from a private queue of prefilter survivors.  When a
+// tile's starts are used up the warp stages the next tile into the other
+// buffer while lanes that are still enumerating on the old one carry on, so
+// neither a block-wide barrier nor the end of a tile ever idles the lanes
+// (a buffer is recycled only once no lane works in it).
+// FULL = false compiles the machine for plans made of single strands and proper
+// helices only (most descriptors): the pseudoknot / parallel helix / triplex /
+// quadruplex code is left out, which keeps the hot loop inside the
+// instruction cache.
+template <int MODE, bool FULL>
 __global__ void gm_search_kernel(const ScanArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -166,20 +174,24 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	const int stage_bytes = ((Lbytes >> 1) + 32 + 15) & ~15; // packed staging (+ alignment slack)
 	const int nwb = ((Lbytes + 31) >> 5) + 4;
 	const int n_dups = c_par.n_dups;
+	const int NBUF = MODE == 0 ? 2 : 1;
 
-	// carve shared memory (mirrors smem_need() on the host)
-	Smem *sm = reinterpret_cast<Smem *>(smem_raw);
-	uint8_t *p = smem_raw + 64;
-	uint8_t *sm_stage = p;               p += stage_bytes;
-	uint8_t *sm_fwd = p;                 p += Lbytes;
-	uint8_t *sm_rc = p;                  p += Lbytes;
-	uint32_t *sm_pb = reinterpret_cast<uint32_t *>(p);         p += (((size_t)2 * n_dups * 4 * nwb * 4) + 15) & ~(size_t)15;
+	// carve shared memory (mirrors smem_need() on the host): plan tables shared
+	// by the block, then one private region per warp, then the lane state
+	const int nwarps = nt >> 5;
+	const size_t pb_bytes = (((size_t)2 * n_dups * 4 * nwb * 4) + 15) & ~(size_t)15;
+	const size_t buf_bytes = 2 * (size_t)Lbytes + pb_bytes + (GM_REC_CACHE + 2) * 8;
+	const size_t warp_bytes = 16 + (size_t)stage_bytes + NBUF * buf_bytes + GM_QCAP * 2;
+	uint8_t *p = smem_raw;
 	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
 	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
 	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
-	int64_t *sm_rec = reinterpret_cast<int64_t *>(p);          p += (GM_REC_CACHE + 1) * 8;
-	uint16_t *sm_q = reinterpret_cast<uint16_t *>(p);          p += (size_t)(nt >> 5) * GM_QCAP * 2;
+	uint8_t *wp = p + (size_t)warp * warp_bytes;               p += (size_t)nwarps * warp_bytes;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
+	WarpTile *sm = reinterpret_cast<WarpTile *>(wp);           wp += 16;
+	uint8_t *sm_stage = wp;                                    wp += stage_bytes;
+	uint8_t *bufs = wp;                                        wp += NBUF * buf_bytes;
+	uint16_t *myq = reinterpret_cast<uint16_t *>(wp);
 
 	// stage the hot plan tables
 	for (int i = tid; i < NS * (int)(sizeof(DevSearch) / 4); i += nt)
@@ -188,7 +200,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		reinterpret_cast<uint32_t *>(sm_ps)[i] = reinterpret_cast<const uint32_t *>(c_plan.pairsets)[i];
 	for (int i = tid; i < ND; i += nt)
 		sm_elmm[i] = pk16(c_plan.elems[i].minlen, c_plan.elems[i].maxlen);
-	if (tid == 0)
+	if (lane == 0)
 		mbar_init(&sm->bar, 1);
 
 	Lane L;
@@ -199,7 +211,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	L.NS = NS;
 	L.ND = ND;
 	L.el_base = NS + c_par.frame_words;
-	L.sq = sm_fwd;
+	L.sq = bufs;
 	L.szero = L.slen = L.comp = 0;
 	L.rec = 0;
 	L.seq = 0;
@@ -208,65 +220,78 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	if (MODE == 0) {
 		for (int d = 0; d < ND; d++) {
 			unmark(L, d);
-			set_cnt(L, d, GM_UNDEF, GM_UNDEF);
+			if (FULL)
+				set_cnt(L, d, GM_UNDEF, GM_UNDEF);
 		}
 	}
-	PairBits pb;
-	pb.base = sm_pb;
-	pb.nwb = nwb;
-	pb.n_dups = n_dups;
-	uint16_t *myq = sm_q + warp * GM_QCAP;
-	__syncthreads();
+	__syncthreads(); // the only block-wide barrier: plan tables are staged
 
 	uint32_t parity = 0;
 	unsigned long long my_starts = 0;
-	int sqbase = 0, strand = 0; // tile index of the lane's window start, strand buffer
 
-	for (;;) {
-		// ---- next tile ------------------------------------------------
-		if (tid == 0)
-			sm->tile = (int64_t)atomicAdd(A.tile_counter, 1ull);
-		__syncthreads();
-		const int64_t t = sm->tile;
-		if (t >= A.n_tiles)
-			break;
-		const int64_t gA = A.g_begin + t * (int64_t)TILE;
-		const int64_t gB = min(gA + (int64_t)TILE, A.g_end);
-		const int64_t lo = gA - H;
+	// current tile (warp-uniform)
+	int cur = NBUF - 1;          // buffer of the current tile (first load flips it to 0)
+	bool have_tile = false, no_more_tiles = false;
+	int64_t gA = 0, gB = 0, lo = 0;
+	uint8_t *sm_fwd = bufs, *sm_rc = bufs;
+	int64_t *sm_rec = reinterpret_cast<int64_t *>(bufs);
+	PairBits pb;
+	pb.base = reinterpret_cast<uint32_t *>(bufs);
+	pb.nwb = nwb;
+	pb.n_dups = n_dups;
+	bool one_rec = false;
+	int r_lo = 0;
+	int64_t rec0_off = 0;
+	int rec0_len = 0;
+	int work_next = 0;
+	const int n_work = A.strands * TILE;
+
+	// per lane: where the start it is enumerating lives
+	int sqbase = 0, strand = 0, mybuf = 0;
+	PairBits mypb = pb;
+
+	// stage tile t into buffer b
+	auto load_tile = [&](int b, int64_t t) {
+		uint8_t *bp = bufs + (size_t)b * buf_bytes;
+		sm_fwd = bp;
+		sm_rc = bp + Lbytes;
+		pb.base = reinterpret_cast<uint32_t *>(bp + 2 * (size_t)Lbytes);
+		sm_rec = reinterpret_cast<int64_t *>(bp + 2 * (size_t)Lbytes + pb_bytes);
+		gA = A.g_begin + t * (int64_t)TILE;
+		gB = min(gA + (int64_t)TILE, A.g_end);
+		lo = gA - H;
 		// packed bytes [bs, bs + nbytes) cover nucleotides [lo_c, hi_c)
 		const int64_t lo_c = max(lo, (int64_t)0);
 		const int64_t hi_c = min(lo + Lbytes, A.total_nt);
 		const int64_t bs = (lo_c >> 1) & ~(int64_t)15;
 		const uint32_t nbytes = (uint32_t)((((hi_c + 1) >> 1) - bs + 15) & ~(int64_t)15);
-		if (tid == 0) {
+		if (lane == 0) {
 			mbar_expect_tx(&sm->bar, nbytes);
 			tma_bulk_g2s(sm_stage, A.packed + bs, nbytes, &sm->bar);
 			// the last record starting at or before gA
-			int a = 0, b = A.n_rec; // rec_off[a] <= gA < rec_off[b]
-			while (b - a > 1) {
-				int m = (a + b) >> 1;
+			int a = 0, bb = A.n_rec; // rec_off[a] <= gA < rec_off[bb]
+			while (bb - a > 1) {
+				int m = (a + bb) >> 1;
 				if (A.rec_off[m] <= gA)
 					a = m;
 				else
-					b = m;
+					bb = m;
 			}
 			sm->r_lo = a;
 			sm->one_rec = A.rec_off[a + 1] >= gB;
-			sm->work = 0;
 		}
-		__syncthreads();
-		{
-			// cache the offsets of up to GM_REC_CACHE records from r_lo on
-			const int r_lo = sm->r_lo;
-			for (int i = tid; i <= GM_REC_CACHE; i += nt) {
-				int r = r_lo + i;
-				sm_rec[i] = r <= A.n_rec ? A.rec_off[r] : (int64_t)1 << 62;
-			}
+		__syncwarp();
+		r_lo = sm->r_lo;
+		one_rec = sm->one_rec != 0;
+		// cache the offsets of up to GM_REC_CACHE records from r_lo on
+		for (int i = lane; i <= GM_REC_CACHE; i += 32) {
+			int r = r_lo + i;
+			sm_rec[i] = r <= A.n_rec ? A.rec_off[r] : (int64_t)1 << 62;
 		}
 		mbar_wait(&sm->bar, parity);
 		parity ^= 1;
 		// expand packed nibbles to one byte per nucleotide, both strands
-		for (int i = tid; i < Lbytes; i += nt) {
+		for (int i = lane; i < Lbytes; i += 32) {
 			const int64_t g = lo + i;
 			uint8_t v = (uint8_t)(4 << 4);
 			if (g >= 0 && g < A.total_nt) {
@@ -276,9 +301,10 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			sm_fwd[i] = v;
 			sm_rc[Lbytes - 1 - i] = complement_byte(v);
 		}
-		__syncthreads();
+		__syncwarp();
 		// pair bitsets: one ballot per (strand, table, base) and 32 positions
-		for (int w = warp; w < nwb; w += (nt >> 5)) {
+		uint32_t *pbw = const_cast<uint32_t *>(pb.base);
+		for (int w = 0; w < nwb; w++) {
 			const int i = w * 32 + lane;
 			const int vf = i < Lbytes ? bcode_of(sm_fwd[i]) : 4;
 			const int vr = i < Lbytes ? bcode_of(sm_rc[i]) : 4;
@@ -288,119 +314,129 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					const unsigned bf = __ballot_sync(0xffffffffu, (dup >> (x * 5 + vf)) & 1u);
 					const unsigned br = __ballot_sync(0xffffffffu, (dup >> (x * 5 + vr)) & 1u);
 					if (lane == 0) {
-						sm_pb[((size_t)(0 * n_dups + dd) * 4 + x) * nwb + w] = bf;
-						sm_pb[((size_t)(1 * n_dups + dd) * 4 + x) * nwb + w] = br;
+						pbw[((size_t)(0 * n_dups + dd) * 4 + x) * nwb + w] = bf;
+						pbw[((size_t)(1 * n_dups + dd) * 4 + x) * nwb + w] = br;
 					}
 				}
 			}
 		}
-		__syncthreads();
+		__syncwarp();
+		rec0_off = sm_rec[0];
+		rec0_len = (int)(sm_rec[1] - sm_rec[0]);
+		work_next = 0;
+		cur = b;
+		have_tile = true;
+	};
 
-		const int n_work = A.strands * TILE;
-		const bool one_rec = sm->one_rec != 0;
-		const int64_t rec0_off = sm_rec[0];
-		const int rec0_len = (int)(sm_rec[1] - sm_rec[0]);
-		int s = 0, ph = PH_IDLE;
-		bool exhausted = false;
-		int qhead = 0, qtail = 0; // warp-uniform
+	// next tile index for this warp, or -1
+	auto next_tile = [&]() -> int64_t {
+		unsigned long long t_ = 0;
+		if (lane == 0)
+			t_ = atomicAdd(A.tile_counter, 1ull);
+		const int64_t t = (int64_t)__shfl_sync(0xffffffffu, t_, 0);
+		return t < A.n_tiles ? t : -1;
+	};
 
-		// locate start item q: returns false if it is not a start of this scan
-		auto locate = [&](int q, int &comp, int &idx, uint32_t &rec, int &slen, int &szero) -> bool {
-			if (q >= n_work)
-				return false;
-			comp = q >= TILE;
-			const int64_t g = gA + (comp ? q - TILE : q);
-			if (g >= gB)
-				return false;
-			int64_t off;
-			if (one_rec) {
-				off = rec0_off;
-				slen = rec0_len;
-				rec = (uint32_t)sm->r_lo;
-			} else if (g < sm_rec[GM_REC_CACHE]) {
-				int a = 0, b = GM_REC_CACHE;
-				while (b - a > 1) {
-					int m = (a + b) >> 1;
-					if (sm_rec[m] <= g)
-						a = m;
-					else
-						b = m;
-				}
-				off = sm_rec[a];
-				slen = (int)(sm_rec[a + 1] - off);
-				rec = (uint32_t)(a + sm->r_lo);
+	// locate start item q of the current tile: false if it is not a start of this scan
+	auto locate = [&](int q, int &comp, int &idx, uint32_t &rec, int &slen, int &szero) -> bool {
+		if (q >= n_work)
+			return false;
+		comp = q >= TILE;
+		const int64_t g = gA + (comp ? q - TILE : q);
+		if (g >= gB)
+			return false;
+		int64_t off;
+		if (one_rec) {
+			off = rec0_off;
+			slen = rec0_len;
+			rec = (uint32_t)r_lo;
+		} else if (g < sm_rec[GM_REC_CACHE]) {
+			int a = 0, b = GM_REC_CACHE;
+			while (b - a > 1) {
+				int m = (a + b) >> 1;
+				if (sm_rec[m] <= g)
+					a = m;
+				else
+					b = m;
+			}
+			off = sm_rec[a];
+			slen = (int)(sm_rec[a + 1] - off);
+			rec = (uint32_t)(a + r_lo);
+		} else {
+			int a = r_lo, b = A.n_rec;
+			while (b - a > 1) {
+				int m = (a + b) >> 1;
+				if (A.rec_off[m] <= g)
+					a = m;
+				else
+					b = m;
+			}
+			off = A.rec_off[a];
+			slen = (int)(A.rec_off[a + 1] - off);
+			rec = (uint32_t)a;
+		}
+		const int pos = (int)(g - off);
+		szero = comp ? slen - 1 - pos : pos;
+		idx = (int)(g - lo);
+		// RM_find_motif searches szero in [0, slen - rm_dminlen], src/find_motif.c:184-205
+		return slen - szero >= c_par.dminlen;
+	};
+
+	// level-0 prefilter of start item q.  v0/have_v0: the candidate mask of
+	// search 0's span ends when they all fit one 64-wide chunk.
+	auto prefilter = [&](int q, uint64_t &v0, int &have_v0) -> bool {
+		int comp, idx, slen, szero;
+		uint32_t rec;
+		v0 = 0;
+		have_v0 = 0;
+		bool pass = locate(q, comp, idx, rec, slen, szero);
+		if (!pass)
+			return false;
+		my_starts++;
+		const DevSearch &S0 = sm_ds[0];
+		const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
+		const int base = comp ? Lbytes - 1 - idx : idx;
+		const int dl = min(W, slen - szero) - 1;
+		if (S0.dupi >= 0 && (S0.flt & 0xff)) {
+			// any span end of search 0 at all?
+			int fsd, lsd;
+			if (S0.kind == K_PK) {
+				fsd = dl;
+				lsd = 2 * S0.minlen - 1;
 			} else {
-				int a = sm->r_lo, b = A.n_rec;
-				while (b - a > 1) {
-					int m = (a + b) >> 1;
-					if (A.rec_off[m] <= g)
-						a = m;
-					else
-						b = m;
-				}
-				off = A.rec_off[a];
-				slen = (int)(A.rec_off[a + 1] - off);
-				rec = (uint32_t)a;
+				fsd = min(dl, S0.maxglen - 1);
+				lsd = S0.minglen - 1;
 			}
-			const int pos = (int)(g - off);
-			szero = comp ? slen - 1 - pos : pos;
-			idx = (int)(g - lo);
-			// RM_find_motif searches szero in [0, slen - rm_dminlen], src/find_motif.c:184-205
-			return slen - szero >= c_par.dminlen;
-		};
+			bool any = false;
+			for (int hi = fsd; hi >= lsd && !any; hi -= 64) {
+				const int l0 = max(lsd, hi - 63);
+				const uint64_t v = wc_mask(pb, sq, comp, base, S0.dupi, S0.flt, 0, l0, hi - l0 + 1);
+				any = v != 0;
+				if (hi == fsd && l0 == lsd && S0.kind != K_PK) {
+					v0 = v;
+					have_v0 = 1;
+				}
+			}
+			pass = any;
+		}
+		if (pass && S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
+			// a seq= without '$' that cannot match the longest
+			// placement cannot match a shorter one
+			pass = rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
+		}
+		return pass;
+	};
 
-		// level-0 prefilter of start item q.  v0/have_v0: the candidate mask of
-		// search 0's span ends when they all fit one 64-wide chunk.
-		auto prefilter = [&](int q, uint64_t &v0, int &have_v0) -> bool {
-			int comp, idx, slen, szero;
-			uint32_t rec;
-			v0 = 0;
-			have_v0 = 0;
-			bool pass = locate(q, comp, idx, rec, slen, szero);
-			if (!pass)
-				return false;
-			my_starts++;
-			const DevSearch &S0 = sm_ds[0];
-			const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
-			const int base = comp ? Lbytes - 1 - idx : idx;
-			const int dl = min(W, slen - szero) - 1;
-			if (S0.dupi >= 0 && (S0.flt & 0xff)) {
-				// any span end of search 0 at all?
-				int fsd, lsd;
-				if (S0.kind == K_PK) {
-					fsd = dl;
-					lsd = 2 * S0.minlen - 1;
-				} else {
-					fsd = min(dl, S0.maxglen - 1);
-					lsd = S0.minglen - 1;
-				}
-				bool any = false;
-				for (int hi = fsd; hi >= lsd && !any; hi -= 64) {
-					const int l0 = max(lsd, hi - 63);
-					const uint64_t v = wc_mask(pb, sq, comp, base, S0.dupi, S0.flt, 0, l0, hi - l0 + 1);
-					any = v != 0;
-					if (hi == fsd && l0 == lsd && S0.kind != K_PK) {
-						v0 = v;
-						have_v0 = 1;
-					}
-				}
-				pass = any;
-			}
-			if (pass && S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
-				// a seq= without '$' that cannot match the longest
-				// placement cannot match a shorter one
-				pass = rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
-			}
-			return pass;
-		};
-
-		if (MODE == 1) {
-			// prefilter only: append the survivors to the global worklist
+	if (MODE == 1) {
+		// prefilter only: append the survivors to the global worklist
+		for (;;) {
+			const int64_t t = next_tile();
+			if (t < 0)
+				break;
+			load_tile(0, t);
 			for (;;) {
-				int chunk = 0;
-				if (lane == 0)
-					chunk = atomicAdd(&sm->work, 32);
-				chunk = __shfl_sync(0xffffffffu, chunk, 0);
+				const int chunk = work_next;
+				work_next += 32;
 				if (chunk >= n_work)
 					break;
 				const int q = chunk + lane;
@@ -429,25 +465,39 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					}
 				}
 			}
-			__syncthreads();
-			continue;
+			__syncwarp();
 		}
+	} else {
+		int s = 0, ph = PH_IDLE;
+		int qhead = 0, qtail = 0; // warp-uniform
 
 		// ---- the machine ------------------------------------------------
 		for (;;) {
 			const unsigned idle = __ballot_sync(0xffffffffu, ph == PH_IDLE);
 			if (idle) {
 				const int want = __popc(idle);
-				// top the queue up: prefilter chunks of 32 start items
-				while (qtail - qhead < want && !exhausted) {
-					int chunk = 0;
-					if (lane == 0)
-						chunk = atomicAdd(&sm->work, 32);
-					chunk = __shfl_sync(0xffffffffu, chunk, 0);
-					if (chunk >= n_work) {
-						exhausted = true;
-						break;
+				// top the queue up: prefilter chunks of 32 start items; when the
+				// tile runs dry move on to the next one in the other buffer
+				while (qtail - qhead < want) {
+					if (!have_tile || work_next >= n_work) {
+						if (no_more_tiles)
+							break;
+						if (qtail != qhead)
+							break; // queued starts still point into the current tile
+						const int nb = (cur + 1) % NBUF;
+						if (__ballot_sync(0xffffffffu, ph != PH_IDLE && mybuf == nb))
+							break; // a lane still enumerates in that buffer
+						const int64_t t = next_tile();
+						if (t < 0) {
+							no_more_tiles = true;
+							have_tile = false;
+							break;
+						}
+						load_tile(nb, t);
+						continue;
 					}
+					const int chunk = work_next;
+					work_next += 32;
 					const int q = chunk + lane;
 					uint64_t v0;
 					int have_v0;
@@ -474,6 +524,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					strand = comp;
 					sqbase = comp ? Lbytes - 1 - idx : idx;
 					L.sq = (comp ? sm_rc : sm_fwd) + sqbase;
+					mybuf = cur;
+					mypb = pb;
 					// RM_find_motif, src/find_motif.c:184-205
 					L_ZD(L, 0) = pk16(0, min(W, slen - szero) - 1);
 					s = 0;
@@ -481,15 +533,16 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				}
 				qhead += min(avail, want);
 				__syncwarp();
-				if (exhausted && qtail == qhead && __all_sync(0xffffffffu, ph == PH_IDLE))
+				if (no_more_tiles && qtail == qhead && __all_sync(0xffffffffu, ph == PH_IDLE))
 					break;
 			}
 
-#define GM_MASK(S, z, clo, n) wc_mask(pb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n))
+#define GM_MASK(S, z, clo, n) wc_mask(mypb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n))
+#define GM_FULL FULL
 #include "gm_machine_body.inc"
+#undef GM_FULL
 #undef GM_MASK
 		}
-		__syncthreads(); // everyone is done with this tile's shared memory
 	}
 
 	// (start, strand) pairs searched, for the stats
@@ -498,7 +551,6 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	if (lane == 0 && my_starts)
 		atomicAdd(A.start_count, my_starts);
 }
-
 
 // First-pair scan used where no pair bitsets exist (gm_dfs_kernel): span ends
 // in [lo, lo+n) whose outermost pair can form -- what match_wchlx tests first
@@ -524,6 +576,7 @@ struct DfsSmem {
 // each new lane's private window (one byte per nucleotide of the searched
 // strand, reverse complement included) straight from the packed database, and
 // the lanes run the same machine as the tile kernel.
+template <bool FULL>
 __global__ void gm_dfs_kernel(const ScanArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -566,7 +619,8 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	L.seq = 0;
 	for (int d = 0; d < ND; d++) {
 		unmark(L, d);
-		set_cnt(L, d, GM_UNDEF, GM_UNDEF);
+		if (FULL)
+			set_cnt(L, d, GM_UNDEF, GM_UNDEF);
 	}
 	uint32_t *went = sm_ent + (size_t)warp * 32 * GM_WL_WORDS;
 	const int wst = c_par.win_stage;          // packed bytes staged per worklist entry
@@ -683,7 +737,9 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 				break;
 		}
 #define GM_MASK(S, z, clo, n) wc_mask_scan(L, (S), (z), (clo), (n))
+#define GM_FULL FULL
 #include "gm_machine_body.inc"
+#undef GM_FULL
 #undef GM_MASK
 	}
 }

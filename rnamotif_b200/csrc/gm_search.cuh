@@ -64,6 +64,10 @@ struct DevParams {
 	int win_stage;          // split path: packed bytes staged per worklist entry (multiple of 16)
 	int n_dups;             // distinct duplex tables with pair bitsets
 	unsigned dups[GM_MAX_DUPS];
+	int lite;               // plan of single strands and proper helices only: the lane
+	                        // state has no per-element counter words; the sink reads the
+	                        // mispair / mismatch counts from the frames through elsrc[]
+	int elsrc[GM_MAX_DESCR]; // lite: search whose frame word 1 holds element d's count
 };
 
 // frame words: 0 (sd, lsd)  1 (flags, resume phase)  2 (s5, s3)  3 (s3lim, hl)
@@ -135,7 +139,7 @@ __device__ __forceinline__ void set_mpr(Lane &L, int d, int mpr)
 // Boolean result only: for the operator subset the plan admits (classes, '.',
 // '*', \{m,n\}, '^', '$') "some backtracking path succeeds" is regular-language
 // membership, which the position automaton decides exactly.
-__device__ int rx_match(const gm_regex_t &rx, const uint8_t *s, int n)
+__device__ __noinline__ int rx_match(const gm_regex_t &rx, const uint8_t *s, int n)
 {
 	const uint64_t skip = rx.skip, star = rx.star;
 	const uint64_t accept = (uint64_t)1 << rx.npos;
@@ -168,7 +172,7 @@ __device__ int rx_match(const gm_regex_t &rx, const uint8_t *s, int n)
 // mm_step/mm_advance, src/mm_regexp.c:353-469 (fixed-length patterns).
 // Returns 1 and the mismatch count of the first (leftmost) placement that
 // stays within l_mm.
-__device__ int rx_match_mm(const gm_regex_t &rx, const uint8_t *s, int n, int l_mm, int *n_mm)
+__device__ __noinline__ int rx_match_mm(const gm_regex_t &rx, const uint8_t *s, int n, int l_mm, int *n_mm)
 {
 	const int m = rx.mm_len;
 	const int last = rx.bol ? 0 : n;

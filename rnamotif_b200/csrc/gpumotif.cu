@@ -68,6 +68,7 @@ struct gm_ctx {
 	size_t smem_bytes;
 	// split path (prefilter kernel -> worklist -> dfs kernel)
 	bool use_split;
+	bool full;            // plan needs the pseudoknot / parallel / triplex / quadruplex code
 	int a_threads, a_blocks, b_threads, b_blocks;
 	size_t a_smem, b_smem;
 	uint32_t *d_wl;
@@ -93,6 +94,22 @@ extern "C" int gm_device_count(void)
 		return 0;
 	}
 	return n;
+}
+
+// kernel variants: FULL only when the plan has something besides single strands
+// and proper helices
+typedef void (*search_kernel_t)(const ScanArgs);
+static search_kernel_t fused_kernel(bool full)
+{
+	return full ? (search_kernel_t)gm_search_kernel<0, true> : (search_kernel_t)gm_search_kernel<0, false>;
+}
+static search_kernel_t dfs_kernel(bool full)
+{
+	return full ? (search_kernel_t)gm_dfs_kernel<true> : (search_kernel_t)gm_dfs_kernel<false>;
+}
+static search_kernel_t pre_kernel(void)
+{
+	return (search_kernel_t)gm_search_kernel<1, false>;
 }
 
 // --------------------------------------------------------------- plan checks
@@ -296,7 +313,19 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		}
 	}
 	par->frame_words = fr;
-	par->words_per_lane = NS + fr + 2 * ND;
+	par->lite = 1;
+	for (int s = 0; s < NS; s++)
+		if (ds[s].kind != K_SS && ds[s].kind != K_WC)
+			par->lite = 0;
+	for (int d = 0; d < ND; d++) {
+		const gm_elem_t &e = pl->elems[d];
+		int src = e.searchno;
+		if (e.type == GM_H3 && e.n_mates >= 1)
+			src = pl->elems[e.mates[0]].searchno; // the helix head keeps the count
+		par->elsrc[d] = src >= 0 && src < NS ? src : 0;
+	}
+	// lite plans keep no per-element counter words (see DevParams::lite)
+	par->words_per_lane = NS + fr + (par->lite ? 1 : 2) * ND;
 	return 0;
 }
 
@@ -311,16 +340,17 @@ extern "C" int gm_plan_check(const gm_plan_t *plan)
 
 static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state = true)
 {
+	// mirrors the carve-up at the top of gm_search_kernel
 	const int Lb = (tile + 2 * c->par.halo + 15) & ~15;
-	size_t n = 64;
-	n += ((Lb >> 1) + 32 + 15) & ~15;
-	n += 2 * (size_t)Lb;
-	n += (((size_t)2 * c->par.n_dups * 4 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15;
+	const size_t stage = ((Lb >> 1) + 32 + 15) & ~15;
+	const size_t pb = (((size_t)2 * c->par.n_dups * 4 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15;
+	const size_t buf_bytes = 2 * (size_t)Lb + pb + (GM_REC_CACHE + 2) * 8;
+	const size_t warp_bytes = 16 + stage + (with_state ? 2 : 1) * buf_bytes + GM_QCAP * 2;
+	size_t n = 0;
 	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
 	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
 	n += (c->par.n_descr * 4 + 15) & ~15;
-	n += (GM_REC_CACHE + 1) * 8;
-	n += (size_t)(threads >> 5) * GM_QCAP * 2;
+	n += (size_t)(threads >> 5) * warp_bytes;
 	if (with_state)
 		n += (size_t)c->par.words_per_lane * threads * 4;
 	return n;
@@ -341,27 +371,33 @@ static size_t dfs_smem_need(const gm_ctx *c, int threads)
 
 static int configure_launch(gm_ctx *c, int tile)
 {
-	// pick the largest block that leaves room for >= 2 CTAs per SM
+	// warps are independent (private tile buffers), so small blocks cost nothing
+	// and waste the least shared memory to rounding: pick the block size that
+	// puts the most warps on an SM
 	const size_t smem_sm = 227 * 1024;
 	int best_t = 0;
-	for (int t = 256; t >= 32; t >>= 1) {
-		size_t need = smem_need(c, t, tile);
-		if (need <= smem_sm / 2 || (t == 32 && need <= smem_sm)) {
+	size_t best_warps = 0;
+	for (int t = 64; t <= 256; t <<= 1) {
+		size_t need = smem_need(c, t, tile) + 1024; // + per-block reservation
+		if (need > smem_sm)
+			continue;
+		size_t warps = std::min<size_t>(smem_sm / need * (t / 32), 64);
+		if (warps > best_warps) {
+			best_warps = warps;
 			best_t = t;
-			break;
 		}
 	}
-	if (best_t == 0) {
-		// shrink the tile
+	if (best_t == 0 && smem_need(c, 32, tile) + 1024 <= smem_sm)
+		best_t = 32;
+	if (best_t == 0)
 		return fail("plan needs %zu bytes of shared memory per 32-lane block (limit %zu)",
 			    smem_need(c, 32, tile), smem_sm);
-	}
 	c->threads = best_t;
 	c->par.tile = tile;
 	c->smem_bytes = smem_need(c, best_t, tile);
-	CU(cudaFuncSetAttribute(gm_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+	CU(cudaFuncSetAttribute(fused_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
 	int per_sm = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gm_search_kernel<0>, c->threads, c->smem_bytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel(c->full), c->threads, c->smem_bytes));
 	if (per_sm < 1)
 		return fail("search kernel does not fit on an SM (threads %d, smem %zu)", c->threads, c->smem_bytes);
 	c->blocks = per_sm * c->n_sm;
@@ -397,8 +433,8 @@ static int configure_launch(gm_ctx *c, int tile)
 			if (need > smem_sm)
 				continue;
 			int n = 0;
-			if (cudaFuncSetAttribute(gm_dfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
-			    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gm_dfs_kernel, t, need) != cudaSuccess)
+			if (cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
+			    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dfs_kernel(c->full), t, need) != cudaSuccess)
 				continue;
 			if (n * t > best_w) {
 				best_w = n * t;
@@ -410,9 +446,9 @@ static int configure_launch(gm_ctx *c, int tile)
 		cudaGetLastError();
 		int na = 0;
 		if (c->b_threads > 0 && c->a_smem <= smem_sm &&
-		    cudaFuncSetAttribute(gm_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
-		    cudaFuncSetAttribute(gm_dfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->b_smem) == cudaSuccess &&
-		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, gm_search_kernel<1>, c->a_threads, c->a_smem) == cudaSuccess &&
+		    cudaFuncSetAttribute(pre_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
+		    cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->b_smem) == cudaSuccess &&
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(), c->a_threads, c->a_smem) == cudaSuccess &&
 		    na >= 1) {
 			c->a_blocks = na * c->n_sm;
 			c->use_split = true;
@@ -450,6 +486,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 		return -1;
 	}
 	c->plan = *plan;
+	c->full = !c->par.lite;
 	int n = gm_device_count();
 	if (n <= 0) {
 		delete c;
@@ -490,7 +527,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	cudaMemcpyToSymbolAsync(c_plan, &c->plan, sizeof c->plan, 0, cudaMemcpyHostToDevice, c->stream);
 	cudaMemcpyToSymbolAsync(c_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, 0, cudaMemcpyHostToDevice, c->stream);
 	g_const_owner[device < 64 ? device : 63] = device < 64 ? c : NULL;
-	if (configure_launch(c, 4096)) {
+	if (configure_launch(c, 1024)) {
 		gm_ctx_destroy(c);
 		return -1;
 	}
@@ -698,7 +735,7 @@ static int launch(gm_ctx *c)
 	CU(cudaEventRecord(c->ev[3], c->stream));
 	if (A.n_tiles > 0 && !c->use_split) {
 		int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
-		gm_search_kernel<0><<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+		fused_kernel(c->full)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 		CU(cudaGetLastError());
 		c->stats.n_launches++;
 	} else if (A.n_tiles > 0) {
@@ -721,9 +758,9 @@ static int launch(gm_ctx *c)
 			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
 			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
 			int ablocks = (int)std::min<int64_t>(c->a_blocks, A.n_tiles);
-			gm_search_kernel<1><<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
+			pre_kernel()<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
-			gm_dfs_kernel<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
+			dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
 			c->stats.n_launches += 2;
 		}
