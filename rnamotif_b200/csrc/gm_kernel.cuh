@@ -22,7 +22,7 @@ __constant__ gm_plan_t c_plan;
 __constant__ DevSearch c_ds[GM_MAX_DESCR];
 __constant__ DevParams c_par;
 
-#define GM_REC_CACHE 62
+#define GM_REC_CACHE 30
 
 struct ScanArgs {
 	const uint8_t *packed;      // 4-bit codes, nucleotide g in byte g>>1, nibble g&1
@@ -137,11 +137,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 
 // -------------------------------------------------------------- the sink
 
+__device__ __noinline__ uint32_t el_word_lite(const Lane &L, int d)
+{
+	const int s = c_par.elsrc[d];
+	const int type = c_plan.elems[d].type;
+	const int z = lo16(L_ZD(L, s));
+	if (type == GM_SS)
+		return pk16(z, lo16(L_FR(L, s, 0)) - z + 1);
+	const int hl = hi16(L_FR(L, s, 3));
+	if (type == GM_H5)
+		return pk16(z, hl);
+	return pk16(hi16(L_FR(L, s, 2)) - hl + 1, hl); // H3
+}
+__device__ __forceinline__ int m_off(const Lane &L, int d) { return lo16(el_word(L, d, c_par.lite != 0)); }
+__device__ __forceinline__ int m_len(const Lane &L, int d) { return hi16(el_word(L, d, c_par.lite != 0)); }
+
 // element type covering window-relative position p, or -1 (fm_window == UNDEF)
 __device__ __noinline__ int wtype(const Lane &L, int p)
 {
 	for (int d = 0; d < L.ND; d++) {
-		uint32_t w = L_EL(L, d);
+		uint32_t w = el_word(L, d, c_par.lite != 0);
 		int off = lo16(w), len = hi16(w);
 		if (len > 0 && p >= off && p < off + len)
 			return c_plan.elems[d].type;
@@ -316,7 +331,7 @@ __device__ __noinline__ void sink(Lane &L, const ScanArgs &A)
 	h[6] = (uint32_t)ctx[2];
 	h[7] = (uint32_t)ctx[3];
 	for (int d = 0; d < L.ND; d++) {
-		const uint32_t el = L_EL(L, d);
+		const uint32_t el = el_word(L, d, c_par.lite != 0);
 		int mpr, mm;
 		if (c_par.lite) {
 			// counts live in the frames: a helix head keeps its mispairs, an ss its mismatches

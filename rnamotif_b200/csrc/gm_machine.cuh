@@ -218,10 +218,9 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	// never-marked elements read as UNDEF; counters start at UNDEF like
 	// SE_init leaves them (src/compile.c:570-571)
 	if (MODE == 0) {
-		for (int d = 0; d < ND; d++) {
+		for (int d = 0; FULL && d < ND; d++) {
 			unmark(L, d);
-			if (FULL)
-				set_cnt(L, d, GM_UNDEF, GM_UNDEF);
+			set_cnt(L, d, GM_UNDEF, GM_UNDEF);
 		}
 	}
 	__syncthreads(); // the only block-wide barrier: plan tables are staged
@@ -617,10 +616,9 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	L.szero = L.slen = L.comp = 0;
 	L.rec = 0;
 	L.seq = 0;
-	for (int d = 0; d < ND; d++) {
+	for (int d = 0; FULL && d < ND; d++) {
 		unmark(L, d);
-		if (FULL)
-			set_cnt(L, d, GM_UNDEF, GM_UNDEF);
+		set_cnt(L, d, GM_UNDEF, GM_UNDEF);
 	}
 	uint32_t *went = sm_ent + (size_t)warp * 32 * GM_WL_WORDS;
 	const int wst = c_par.win_stage;          // packed bytes staged per worklist entry

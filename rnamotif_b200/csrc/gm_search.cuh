@@ -124,8 +124,15 @@ __device__ __forceinline__ void unmark(Lane &L, int d)
 {
 	L_EL(L, d) = pk16(GM_UNDEF, GM_UNDEF);
 }
-__device__ __forceinline__ int m_off(const Lane &L, int d) { return lo16(L_EL(L, d)); }
-__device__ __forceinline__ int m_len(const Lane &L, int d) { return hi16(L_EL(L, d)); }
+// (s_matchoff, s_matchlen) of element d as one packed word.  Plans with
+// pseudoknots etc. keep them in the lane state (find_minlen/find_maxlen read
+// them during the search); "lite" plans do not store them at all -- they are
+// only needed at the hit sink, where they follow from the frames.
+__device__ uint32_t el_word_lite(const Lane &L, int d);
+__device__ __forceinline__ uint32_t el_word(const Lane &L, int d, bool lite)
+{
+	return lite ? el_word_lite(L, d) : L_EL(L, d);
+}
 __device__ __forceinline__ void set_cnt(Lane &L, int d, int mpr, int mm)
 {
 	L_EM(L, d) = pk16(mpr, mm);

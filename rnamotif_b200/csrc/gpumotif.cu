@@ -324,8 +324,8 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 			src = pl->elems[e.mates[0]].searchno; // the helix head keeps the count
 		par->elsrc[d] = src >= 0 && src < NS ? src : 0;
 	}
-	// lite plans keep no per-element counter words (see DevParams::lite)
-	par->words_per_lane = NS + fr + (par->lite ? 1 : 2) * ND;
+	// lite plans keep no per-element words at all (see DevParams::lite)
+	par->words_per_lane = NS + fr + (par->lite ? 0 : 2) * ND;
 	return 0;
 }
 
