@@ -527,7 +527,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	cudaMemcpyToSymbolAsync(c_plan, &c->plan, sizeof c->plan, 0, cudaMemcpyHostToDevice, c->stream);
 	cudaMemcpyToSymbolAsync(c_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, 0, cudaMemcpyHostToDevice, c->stream);
 	g_const_owner[device < 64 ? device : 63] = device < 64 ? c : NULL;
-	if (configure_launch(c, 1024)) {
+	if (configure_launch(c, 768)) {
 		gm_ctx_destroy(c);
 		return -1;
 	}
