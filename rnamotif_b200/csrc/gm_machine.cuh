@@ -127,6 +127,17 @@ __device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, i
 	if (dupi < 0 || req == 0)
 		return ones;
 	const uint32_t *sets = pb.base + ((size_t)(strand * pb.n_dups + dupi) * 4) * pb.nwb;
+	if (budget == 0 && first_must) {
+		// the common case (no mispairs, paired ends): a plain AND chain
+		uint64_t a = ones;
+		for (int k = 0; k < req; k++) {
+			const int x = bcode_of(sq[z + k]);
+			if (x >= 4)
+				return 0;
+			a &= bits64(sets + x * pb.nwb, sqbase + lo - k);
+		}
+		return a;
+	}
 	uint64_t a0 = ones, a1 = ones, a2 = ones;
 	for (int k = 0; k < req; k++) {
 		const int x = bcode_of(sq[z + k]);
@@ -396,22 +407,26 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
 		const int base = comp ? Lbytes - 1 - idx : idx;
 		const int dl = min(W, slen - szero) - 1;
-		if (S0.dupi >= 0 && (S0.flt & 0xff)) {
-			// any span end of search 0 at all?
+		if (c_par.pf_search >= 0) {
+			// any span end at all for the first helix of the descriptor?  (It is
+			// search 0, or follows fixed-length single strands, so its 5' start
+			// pz is known.)
+			const DevSearch &SP = sm_ds[c_par.pf_search];
+			const int pz = c_par.pf_z;
 			int fsd, lsd;
-			if (S0.kind == K_PK) {
+			if (SP.kind == K_PK) {
 				fsd = dl;
-				lsd = 2 * S0.minlen - 1;
+				lsd = pz + 2 * SP.minlen - 1;
 			} else {
-				fsd = min(dl, S0.maxglen - 1);
-				lsd = S0.minglen - 1;
+				fsd = min(dl, pz + SP.maxglen - 1);
+				lsd = pz + SP.minglen - 1;
 			}
 			bool any = false;
 			for (int hi = fsd; hi >= lsd && !any; hi -= 64) {
 				const int l0 = max(lsd, hi - 63);
-				const uint64_t v = wc_mask(pb, sq, comp, base, S0.dupi, S0.flt, 0, l0, hi - l0 + 1);
+				const uint64_t v = wc_mask(pb, sq, comp, base, SP.dupi, SP.flt, pz, l0, hi - l0 + 1);
 				any = v != 0;
-				if (hi == fsd && l0 == lsd && S0.kind != K_PK) {
+				if (hi == fsd && l0 == lsd && SP.kind != K_PK && c_par.pf_search == 0) {
 					v0 = v;
 					have_v0 = 1;
 				}

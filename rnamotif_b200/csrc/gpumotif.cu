@@ -313,6 +313,28 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		}
 	}
 	par->frame_words = fr;
+	// level-0 prefilter: the first helix head, if everything before it is a
+	// fixed-length single strand without seq= (then its 5' start is known)
+	par->pf_search = -1;
+	par->pf_z = 0;
+	{
+		int z = 0;
+		for (int s = 0; s < NS; s++) {
+			const DevSearch &S = ds[s];
+			if (S.kind == K_SS) {
+				if (S.minlen != S.maxlen || S.rx5 >= 0 || S.next_s != s + 1 || !S.loop)
+					break;
+				z += S.minlen;
+				continue;
+			}
+			if ((S.kind == K_WC || S.kind == K_QU || S.kind == K_PK) && S.dupi >= 0 && (S.flt & 0xff) > 0 &&
+			    (S.kind != K_PK || pl->elems[S.d].scope == 0)) {
+				par->pf_search = s;
+				par->pf_z = z;
+			}
+			break;
+		}
+	}
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
 		if (ds[s].kind != K_SS && ds[s].kind != K_WC)
@@ -412,7 +434,7 @@ static int configure_launch(gm_ctx *c, int tile)
 	c->par.win_stride = words * 4;
 	c->par.win_stage = (((wtot + 1) / 2 + 1 + 15 + 15) & ~15);
 	bool eligible = wtot <= 512 &&
-		((S0.dupi >= 0 && (S0.flt & 0xff) > 0) ||
+		(c->par.pf_search >= 0 ||
 		 (S0.rx5 >= 0 && S0.mm5 == 0 && !c->plan.regex[S0.rx5].eol));
 	// The fused kernel is the default: on the measured configurations it is the
 	// faster of the two (profiles/README.md).  GPUMOTIF_PATH=split selects the
