@@ -59,7 +59,7 @@ def full(path):
                          capture_output=True, text=True).stdout
     cur, out = None, []
     for r in csv.reader(src.splitlines()):
-        if len(r) >= 2 and r[0] == "File Name":
+        if len(r) >= 2 and r[0] in ("File Name", "File Path"):
             cur = r[1].split("/")[-1]
             continue
         if len(r) < 9 or r[0] in ("Line No", ""):

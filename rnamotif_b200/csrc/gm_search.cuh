@@ -46,8 +46,13 @@ struct DevSearch {
 	int fr;                // word offset of this search's frame in the lane state
 	int dupi;              // index of `duplex` in DevParams::dups (pair bitsets), or -1
 	int flt;               // span-end prefilter: req | budget << 8 | first_must << 16
+	// look-ahead pruning: the next helix head reachable through fixed-length single
+	// strands, as first interior element (kid) and as following sibling (sib), with
+	// the nucleotides in between; -1 if there is none
+	int kid_t, kid_off;
+	int sib_t, sib_off;
 };
-static_assert(sizeof(DevSearch) == 23 * 4, "DevSearch is staged with an odd word stride");
+static_assert(sizeof(DevSearch) == 27 * 4, "DevSearch is staged with an odd word stride");
 
 #define GM_MAX_DUPS 8
 

@@ -313,6 +313,31 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		}
 	}
 	par->frame_words = fr;
+	// look-ahead targets (see DevSearch::kid_t / sib_t)
+	for (int s = 0; s < NS; s++) {
+		DevSearch &S = ds[s];
+		S.kid_t = S.sib_t = -1;
+		S.kid_off = S.sib_off = 0;
+		if (S.kind != K_WC)
+			continue;
+		for (int which = 0; which < 2; which++) {
+			int u = which == 0 ? s + 1 : S.next_s, off = 0;
+			while (u >= 0 && u < NS && ds[u].kind == K_SS && ds[u].minlen == ds[u].maxlen &&
+			       ds[u].rx5 < 0 && ds[u].next_s == u + 1) {
+				off += ds[u].minlen;
+				u++;
+			}
+			if (u >= 0 && u < NS && ds[u].kind == K_WC && ds[u].dupi >= 0 && (ds[u].flt & 0xff) > 0) {
+				if (which == 0) {
+					S.kid_t = u;
+					S.kid_off = off;
+				} else {
+					S.sib_t = u;
+					S.sib_off = off;
+				}
+			}
+		}
+	}
 	// level-0 prefilter: the first helix head, if everything before it is a
 	// fixed-length single strand without seq= (then its 5' start is known)
 	par->pf_search = -1;
