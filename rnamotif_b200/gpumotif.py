@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgpumotif.so")
+LIB_PATH = os.environ.get("GPUMOTIF_LIB") or os.path.join(_HERE, "csrc", "libgpumotif.so")
 
 PLAN_BYTES = 32120
 
