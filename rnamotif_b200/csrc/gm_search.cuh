@@ -69,6 +69,7 @@ struct DevParams {
 	int win_stage;          // split path: packed bytes staged per worklist entry (multiple of 16)
 	int n_dups;             // distinct duplex tables with pair bitsets
 	unsigned dups[GM_MAX_DUPS];
+	int refill_min;         // idle lanes a warp waits for before it hands out new starts
 	int pf_search;          // search whose candidate mask is the level-0 prefilter, or -1
 	int pf_z;               // its 5' start relative to the window (fixed-length ss before it)
 	int lite;               // plan of single strands and proper helices only: the lane

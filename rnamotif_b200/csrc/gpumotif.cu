@@ -364,6 +364,15 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	for (int s = 0; s < NS; s++)
 		if (ds[s].kind != K_SS && ds[s].kind != K_WC)
 			par->lite = 0;
+	// batch size of the lane refill: large when the prefilter leaves short
+	// enumerations (the batch then runs in step), small when they are long
+	{
+		const int flt0 = par->pf_search >= 0 ? ds[par->pf_search].flt : 0;
+		const bool strong = par->pf_search >= 0 && ((flt0 >> 8) & 0xff) == 0 && (flt0 & 0xff) >= 3;
+		par->refill_min = !par->lite ? 4 : strong ? GM_REFILL_MIN : 8;
+	}
+	if (getenv("GPUMOTIF_REFILL") != NULL)
+		par->refill_min = std::max(1, std::min(32, atoi(getenv("GPUMOTIF_REFILL"))));
 	for (int d = 0; d < ND; d++) {
 		const gm_elem_t &e = pl->elems[d];
 		int src = e.searchno;
