@@ -251,12 +251,16 @@ def run_gpu_arm(args):
     # ---- end-to-end leg: host characters in, candidates out, every step -------
     h2d = d2h = 0
 
+    phases = {}
+
     def step_e2e():
         nonlocal h2d, d2h
         ms.upload_ptr(h_chars.data_ptr(), rec_off)
         ms.scan(0, total, strands)
         st = ms.stats()
         h2d, d2h = st.h2d_bytes, st.d2h_bytes
+        phases.update(h2d_ms=st.h2d_ms, pack_ms=st.pack_ms, kernel_ms=st.kernel_ms, d2h_ms=st.d2h_ms,
+                      sort_ms=st.sort_ms)
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -285,7 +289,7 @@ def run_gpu_arm(args):
                        else "input smaller than L2; each step re-reads it after the hit gather",
                        "candidates_per_step_rank0": int(hits_n)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": t_e2e / args.steps},
+                    "ms_per_step": t_e2e / args.steps, "phases_ms_last_step": phases},
             "gpu_launches": int(gpu_launches),
             "roofline": roof,
             "clocks": sampler.summary(),

@@ -47,8 +47,8 @@ typedef struct gm_ctx gm_ctx;
 
 typedef struct gm_scan_stats {
 	double   kernel_ms;      /* search kernel(s), CUDA events on the ctx stream */
-	double   pack_ms;        /* char -> 4-bit pack kernel of the last upload */
-	double   h2d_ms;         /* host -> device copy of the last upload */
+	double   pack_ms;        /* (included in h2d_ms since uploads are chunked) */
+	double   h2d_ms;         /* host -> device copy + pack of the last upload, copy stream */
 	double   d2h_ms;         /* hit gather device -> host */
 	double   sort_ms;        /* host sort into enumeration order */
 	uint64_t n_starts;       /* (start, strand) pairs searched */
@@ -77,7 +77,10 @@ int gm_plan_check(const gm_plan_t *plan);
  * buffer (src/dbutil.c:42-128: letters only, any case, u or t): record r is
  * seq[rec_off[r] .. rec_off[r+1]).  The copy goes host -> device as is and is
  * packed to 4-bit IUPAC codes on the device.  `seq` may be pinned or pageable
- * host memory.  Replaces the previous batch. */
+ * host memory.  Replaces the previous batch.  The copy is ASYNCHRONOUS when
+ * `seq` is pinned: it is cut into chunks on a copy stream and the first gm_scan
+ * after it starts searching chunk 0 while the rest is still in flight, so `seq`
+ * must stay valid and unchanged until that scan has returned. */
 int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec);
 
 /* Same, for characters that already live in device memory (a CUDA device

@@ -48,8 +48,15 @@ struct gm_ctx {
 	DevSearch ds[GM_MAX_DESCR];
 	int device;
 	int n_sm;
-	cudaStream_t stream;
+	cudaStream_t stream;       // search kernels, hit gather
+	cudaStream_t copy_stream;  // uploads: H2D copies + pack kernels, in chunks
 	cudaEvent_t ev[6];
+	// an upload is cut into chunks; chunk_ev[i] fires when chunk i is packed, so the
+	// first scan after an upload starts on chunk 0 while the rest is still copying
+	std::vector<cudaEvent_t> chunk_ev;
+	std::vector<int64_t> chunk_end;  // nucleotide offsets where the chunks end
+	bool upload_fresh;               // no scan has consumed the last upload yet
+	cudaEvent_t up_ev[2];            // upload start / end on copy_stream
 	// database
 	uint8_t *d_chars;      // staging for uploaded characters
 	size_t chars_cap;
@@ -570,13 +577,19 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->n_sm = prop.multiProcessorCount;
 	c->stride_words = (int)((sizeof(gm_hit_hdr_t) + plan->n_descr * sizeof(gm_hit_el_t)) / 4);
 	c->hit_cap = (size_t)1 << 20;
-	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+	c->copy_stream = NULL;
+	c->upload_fresh = false;
+	c->up_ev[0] = c->up_ev[1] = NULL;
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
 		delete c;
 		return fail("cudaStreamCreate failed");
 	}
+	cudaEventCreate(&c->up_ev[0]);
+	cudaEventCreate(&c->up_ev[1]);
 	for (int i = 0; i < 6; i++)
 		cudaEventCreate(&c->ev[i]);
-	if (cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+	if (cudaMalloc(&c->d_counters, 32 * sizeof(unsigned long long)) != cudaSuccess) {
 		gm_ctx_destroy(c);
 		return fail("cudaMalloc(counters) failed");
 	}
@@ -604,6 +617,15 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 		g_const_owner[c->device] = NULL;
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
+	if (c->copy_stream)
+		cudaStreamSynchronize(c->copy_stream);
+	for (cudaEvent_t e : c->chunk_ev)
+		cudaEventDestroy(e);
+	for (int i = 0; i < 2; i++)
+		if (c->up_ev[i])
+			cudaEventDestroy(c->up_ev[i]);
+	if (c->copy_stream)
+		cudaStreamDestroy(c->copy_stream);
 	cudaFree(c->d_chars);
 	cudaFree(c->d_packed);
 	cudaFree(c->d_rec_off);
@@ -673,24 +695,48 @@ static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
 		return -1;
 	c->rec_cap = cap_bytes / sizeof(int64_t);
 	CU(cudaMemcpyAsync(c->d_rec_off, c->rec_off.data(), (size_t)(n_rec + 1) * sizeof(int64_t),
-			   cudaMemcpyHostToDevice, c->stream));
+			   cudaMemcpyHostToDevice, c->copy_stream));
 	return 0;
 }
 
-static int pack_on_device(gm_ctx *c, const uint8_t *d_chars)
+// Enqueue the upload on copy_stream in chunks: [H2D copy of chunk i,] pack chunk i,
+// record chunk_ev[i].  Returns without waiting.
+static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src)
 {
 	const int64_t n = c->total_nt;
 	const size_t pbytes = (size_t)(((n + 15) / 16) * 8) + 1024; // slack: kernels read whole 16-byte groups past the end
 	if (ensure((void **)&c->d_packed, &c->packed_cap, pbytes))
 		return -1;
-	CU(cudaEventRecord(c->ev[1], c->stream));
-	if (n > 0) {
-		int64_t groups = (n + 15) / 16;
-		int blocks = (int)std::min<int64_t>((groups + 255) / 256, (int64_t)c->n_sm * 16);
-		gm_pack_kernel<<<blocks, 256, 0, c->stream>>>(d_chars, c->d_packed, n);
-		CU(cudaGetLastError());
+	if (h_chars != NULL && ensure((void **)&c->d_chars, &c->chars_cap, (size_t)n + 64))
+		return -1;
+	// chunk size: at least 64 Mnt, at most 4 chunks (every chunk costs a kernel
+	// launch with its own ramp and tail), a multiple of 16 nucleotides
+	int64_t chunk = std::max<int64_t>((int64_t)64 << 20, (n + 3) / 4);
+	chunk = (chunk + 15) & ~(int64_t)15;
+	const int n_chunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
+	while ((int)c->chunk_ev.size() < n_chunks) {
+		cudaEvent_t e;
+		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		c->chunk_ev.push_back(e);
 	}
-	CU(cudaEventRecord(c->ev[2], c->stream));
+	c->chunk_end.clear();
+	CU(cudaEventRecord(c->up_ev[0], c->copy_stream));
+	for (int i = 0; i < n_chunks; i++) {
+		const int64_t o = (int64_t)i * chunk, len = std::min<int64_t>(chunk, n - o);
+		const uint8_t *src = d_src;
+		if (h_chars != NULL) {
+			CU(cudaMemcpyAsync(c->d_chars + o, h_chars + o, (size_t)len, cudaMemcpyHostToDevice, c->copy_stream));
+			src = c->d_chars;
+		}
+		const int64_t groups = (len + 15) / 16;
+		const int blocks = (int)std::min<int64_t>((groups + 255) / 256, (int64_t)c->n_sm * 16);
+		gm_pack_kernel<<<blocks, 256, 0, c->copy_stream>>>(src + o, c->d_packed + (o >> 1), len);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(c->chunk_ev[i], c->copy_stream));
+		c->chunk_end.push_back(o + len);
+	}
+	CU(cudaEventRecord(c->up_ev[1], c->copy_stream));
+	c->upload_fresh = true;
 	return 0;
 }
 
@@ -698,26 +744,17 @@ extern "C" int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec
 {
 	if (c == NULL)
 		return fail("ctx is NULL");
+	if (c->pending)
+		return fail("a scan is in flight");
 	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->copy_stream)); // the previous upload's staging is reused
 	if (set_records(c, rec_off, n_rec))
 		return -1;
-	const int64_t n = c->total_nt;
-	if (n > 0 && seq == NULL)
+	if (c->total_nt > 0 && seq == NULL)
 		return fail("seq is NULL");
-	if (ensure((void **)&c->d_chars, &c->chars_cap, (size_t)n + 64))
+	if (upload_chunks(c, (const uint8_t *)seq, NULL))
 		return -1;
-	CU(cudaEventRecord(c->ev[0], c->stream));
-	if (n > 0)
-		CU(cudaMemcpyAsync(c->d_chars, seq, (size_t)n, cudaMemcpyHostToDevice, c->stream));
-	if (pack_on_device(c, c->d_chars))
-		return -1;
-	CU(cudaStreamSynchronize(c->stream));
-	float ms = 0;
-	cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-	c->stats.h2d_ms = ms;
-	cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
-	c->stats.pack_ms = ms;
-	c->stats.h2d_bytes = (uint64_t)n + (uint64_t)(n_rec + 1) * 8;
+	c->stats.h2d_bytes = (uint64_t)c->total_nt + (uint64_t)(n_rec + 1) * 8;
 	return 0;
 }
 
@@ -725,19 +762,16 @@ extern "C" int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_
 {
 	if (c == NULL)
 		return fail("ctx is NULL");
+	if (c->pending)
+		return fail("a scan is in flight");
 	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->copy_stream));
 	if (set_records(c, rec_off, n_rec))
 		return -1;
 	if (c->total_nt > 0 && d_seq == NULL)
 		return fail("d_seq is NULL");
-	CU(cudaEventRecord(c->ev[0], c->stream));
-	if (pack_on_device(c, (const uint8_t *)d_seq))
+	if (upload_chunks(c, NULL, (const uint8_t *)d_seq))
 		return -1;
-	CU(cudaStreamSynchronize(c->stream));
-	float ms = 0;
-	cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
-	c->stats.pack_ms = ms;
-	c->stats.h2d_ms = 0;
 	c->stats.h2d_bytes = (uint64_t)(n_rec + 1) * 8;
 	return 0;
 }
@@ -768,7 +802,7 @@ static int launch(gm_ctx *c)
 	if (c->d_hits == NULL) {
 		CU(cudaMalloc(&c->d_hits, c->hit_cap * (size_t)c->stride_words * 4));
 	}
-	CU(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
+	CU(cudaMemsetAsync(c->d_counters, 0, 32 * sizeof(unsigned long long), c->stream));
 	ScanArgs A;
 	A.packed = c->d_packed;
 	A.total_nt = c->total_nt;
@@ -789,12 +823,43 @@ static int launch(gm_ctx *c)
 	A.wl_head = c->d_counters + 4;
 	A.wl_cap = 0;
 	CU(cudaEventRecord(c->ev[3], c->stream));
-	if (A.n_tiles > 0 && !c->use_split) {
+	const int n_chunks = (int)c->chunk_end.size();
+	if (A.n_tiles > 0 && !c->use_split && c->upload_fresh && n_chunks > 1 && n_chunks <= 16) {
+		// first scan of a fresh upload: one launch per chunk, each gated on its
+		// chunk's event, so the search of chunk i overlaps the copy of chunk i+1.
+		// A tile reads `halo` nucleotides past its last start, so launch i stops
+		// that far before the end of chunk i.
+		int64_t lo = c->p_begin;
+		for (int i = 0; i < n_chunks && lo < c->p_end; i++) {
+			int64_t hi = i == n_chunks - 1 ? c->p_end : std::min<int64_t>(c->p_end, c->chunk_end[i] - c->par.halo - c->par.tile);
+			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[i], 0));
+			if (hi <= lo)
+				continue;
+			// whole tiles only, except for the last launch
+			if (i != n_chunks - 1)
+				hi = lo + (hi - lo) / c->par.tile * c->par.tile;
+			if (hi <= lo)
+				continue;
+			A.g_begin = lo;
+			A.g_end = hi;
+			A.n_tiles = (hi - lo + c->par.tile - 1) / c->par.tile;
+			A.tile_counter = c->d_counters + 8 + i;
+			int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
+			fused_kernel(c->full)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+			CU(cudaGetLastError());
+			c->stats.n_launches++;
+			lo = hi;
+		}
+	} else if (A.n_tiles > 0 && !c->use_split) {
+		if (n_chunks > 0)
+			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
 		int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
 		fused_kernel(c->full)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 		CU(cudaGetLastError());
 		c->stats.n_launches++;
 	} else if (A.n_tiles > 0) {
+		if (n_chunks > 0)
+			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
 		// split path, one (prefilter, dfs) launch pair per segment of the range
 		const int64_t seg = std::min<int64_t>(c->seg_nt, c->p_end - c->p_begin);
 		const size_t need = (size_t)seg * c->p_strands;
@@ -822,6 +887,7 @@ static int launch(gm_ctx *c)
 		}
 	}
 	CU(cudaEventRecord(c->ev[4], c->stream));
+	c->upload_fresh = false;
 	return 0;
 }
 
@@ -869,6 +935,11 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 		float ms = 0;
 		cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
 		c->stats.kernel_ms += ms;
+		if (cudaEventQuery(c->up_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->up_ev[0], c->up_ev[1]) == cudaSuccess) {
+			c->stats.h2d_ms = ms;   // copy + pack of the last upload, as enqueued on the copy stream
+			c->stats.pack_ms = 0;
+		}
+		cudaGetLastError();
 		if (cnt[1] <= c->hit_cap)
 			break;
 		// the hit buffer was too small: nothing is lost, run again with room

@@ -134,6 +134,7 @@ class MotifSearch:
         """seq: uint8 array of sequence characters (host), rec_off: int64 offsets."""
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+        self._keep = seq  # the upload is asynchronous: keep the buffer alive until the next scan
         self._ck(lib().gm_db_upload_chars(self._ctx, seq.ctypes.data, rec_off.ctypes.data, len(rec_off) - 1),
                  "gm_db_upload_chars")
 
