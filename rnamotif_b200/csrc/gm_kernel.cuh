@@ -412,7 +412,7 @@ __device__ __noinline__ int pk_minlen(const Lane &L, const uint32_t *elmm, int f
 {
 	int v = 0;
 	for (int d = fd; d <= ld; d++) {
-		int ml = m_len(L, d);
+		const int ml = hi16(L_EL(L, d)); // only plans that keep element words get here
 		v += ml != GM_UNDEF ? ml : lo16(elmm[d]);
 	}
 	return v;
@@ -421,7 +421,7 @@ __device__ __noinline__ int pk_maxlen(const Lane &L, const uint32_t *elmm, int f
 {
 	int v = 0;
 	for (int d = fd; d <= ld; d++) {
-		int ml = m_len(L, d);
+		const int ml = hi16(L_EL(L, d));
 		v += ml != GM_UNDEF ? ml : hi16(elmm[d]);
 	}
 	return v;

@@ -82,7 +82,8 @@ struct DevParams {
 //              4 kind-specific  5,6 span-end candidate mask (PK: 5 = (l_s3, i_minl), 7,8 = mask)
 #define GM_FW_SS 2
 #define GM_FW_HX 7
-#define GM_FW_PK 9
+#define GM_FW_QU 9
+#define GM_FW_PK 16 // 9..15: find_minlen/find_maxlen results, constant while the level is active
 
 __device__ __forceinline__ uint32_t pk16(int a, int b)
 {

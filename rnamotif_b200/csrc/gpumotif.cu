@@ -290,7 +290,7 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	for (int s = 0; s < NS; s++) {
 		DevSearch &S = ds[s];
 		S.fr = fr;
-		fr += S.kind == K_SS ? GM_FW_SS : (S.kind == K_PK || S.kind == K_QU) ? GM_FW_PK : GM_FW_HX;
+		fr += S.kind == K_SS ? GM_FW_SS : S.kind == K_PK ? GM_FW_PK : S.kind == K_QU ? GM_FW_QU : GM_FW_HX;
 		S.dupi = -1;
 		S.flt = 0;
 		if (S.kind == K_WC || S.kind == K_QU || S.kind == K_PK) {
