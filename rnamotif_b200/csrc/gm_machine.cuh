@@ -36,7 +36,7 @@ enum {
 	PHX_IDLE = 0,
 	PHX_ENTER = CL_SPAN * 8, PHX_SPAN, PHX_SS_RESUME, PHX_PH_RESUME, PHX_WC_RESUME,
 	PHX_WX_BEGIN = CL_WX * 8, PHX_WX_RESUME, PHX_WX_FIRST, PHX_WX_EXT,
-	PHX_PK_S5 = CL_PK * 8, PHX_PK_S3,
+	PHX_PK_S5 = CL_PK * 8, PHX_PK_S3, PHX_PK_SD,
 	PHX_TR_RESUME = CL_TR * 8, PHX_TR_S,
 	PHX_QU_S1 = CL_QU * 8, PHX_QU_RESUME, PHX_QU_S2
 };
@@ -53,6 +53,7 @@ enum {
 #define PH_WX_EXT PHX_WX_EXT
 #define PH_PK_S5 PHX_PK_S5
 #define PH_PK_S3 PHX_PK_S3
+#define PH_PK_SD PHX_PK_SD
 #define PH_TR_RESUME PHX_TR_RESUME
 #define PH_TR_S PHX_TR_S
 #define PH_QU_S1 PHX_QU_S1
