@@ -432,8 +432,46 @@ static size_t dfs_smem_need(const gm_ctx *c, int threads)
 	return n;
 }
 
+// Resident warps per SM for a block size and tile, from the occupancy API
+// (registers and shared memory both count), 0 if it does not fit.
+static int warps_per_sm(gm_ctx *c, int threads, int tile)
+{
+	const size_t need = smem_need(c, threads, tile);
+	if (need + 1024 > 227 * 1024)
+		return 0;
+	int n = 0;
+	if (cudaFuncSetAttribute(fused_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
+	    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel(c->full), threads, need) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n * threads / 32;
+}
+
+// Tile size when the caller does not choose one: throughput follows the number
+// of resident warps (the kernel is latency bound) times the share of a staged
+// tile that is not halo, so maximise that product (measured on trna: 640-704).
+static int auto_tile(gm_ctx *c)
+{
+	int best_tile = 256;
+	double best = -1;
+	for (int tile = 256; tile <= 2048; tile += 64) {
+		int w = 0;
+		for (int t = 64; t <= 256; t <<= 1)
+			w = std::max(w, warps_per_sm(c, t, tile));
+		const double score = w * (double)tile / (tile + 2.0 * c->par.halo);
+		if (score > best * 1.001) {
+			best = score;
+			best_tile = tile;
+		}
+	}
+	return best_tile;
+}
+
 static int configure_launch(gm_ctx *c, int tile)
 {
+	if (tile <= 0)
+		tile = auto_tile(c);
 	// warps are independent (private tile buffers), so small blocks cost nothing
 	// and waste the least shared memory to rounding: pick the block size that
 	// puts the most warps on an SM
@@ -441,10 +479,7 @@ static int configure_launch(gm_ctx *c, int tile)
 	int best_t = 0;
 	size_t best_warps = 0;
 	for (int t = 64; t <= 256; t <<= 1) {
-		size_t need = smem_need(c, t, tile) + 1024; // + per-block reservation
-		if (need > smem_sm)
-			continue;
-		size_t warps = std::min<size_t>(smem_sm / need * (t / 32), 64);
+		size_t warps = (size_t)warps_per_sm(c, t, tile);
 		if (warps > best_warps) {
 			best_warps = warps;
 			best_t = t;
@@ -596,7 +631,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	cudaMemcpyToSymbolAsync(c_plan, &c->plan, sizeof c->plan, 0, cudaMemcpyHostToDevice, c->stream);
 	cudaMemcpyToSymbolAsync(c_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, 0, cudaMemcpyHostToDevice, c->stream);
 	g_const_owner[device < 64 ? device : 63] = device < 64 ? c : NULL;
-	if (configure_launch(c, 768)) {
+	if (configure_launch(c, 0)) {
 		gm_ctx_destroy(c);
 		return -1;
 	}
@@ -655,8 +690,8 @@ extern "C" int gm_set_hit_capacity(gm_ctx *c, size_t n)
 
 extern "C" int gm_set_tile(gm_ctx *c, int tile)
 {
-	if (c == NULL || tile < 32 || tile > 32768)
-		return fail("tile must be in [32, 32768]");
+	if (c == NULL || (tile != 0 && (tile < 32 || tile > 32768)))
+		return fail("tile must be 0 (automatic) or in [32, 32768]");
 	CU(cudaSetDevice(c->device));
 	return configure_launch(c, tile);
 }
