@@ -149,11 +149,12 @@ __device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, i
 		uint64_t m = 0;
 		if (x < 4)
 			m = bits64(sets + x * pb.nwb, sqbase + lo - k);
-		if (k == 0) {
-			if (first_must)
-				a0 = a1 = a2 = m;
-			// else: an outermost mispair is always tolerated (ends without 5'
-			// pairing, src/find_motif.c:1014-1017): no constraint from k = 0
+		if (k == 0 && first_must) {
+			a0 = a1 = a2 = m;
+		} else if (k == 0 && budget == 0) {
+			// ends without 5' pairing: an outermost mispair is tolerated even with
+			// no mispair budget (src/find_motif.c:1014-1017 does not test mplim
+			// there); with a budget it simply counts, as below
 		} else {
 			a2 = (a2 & m) | a1;
 			a1 = (a1 & m) | a0;
