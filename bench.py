@@ -230,7 +230,7 @@ def run_gpu_arm(args):
 
     def step_resident():
         nonlocal launches, hits_n
-        ms.scan(0, total, strands)
+        ms.scan(0, total, strands, copy=False)
         st = ms.stats()
         kernel_ms.append(st.kernel_ms)
         launches += st.n_launches
@@ -256,7 +256,7 @@ def run_gpu_arm(args):
     def step_e2e():
         nonlocal h2d, d2h
         ms.upload_ptr(h_chars.data_ptr(), rec_off)
-        ms.scan(0, total, strands)
+        ms.scan(0, total, strands, copy=False)  # candidates are in host memory (library buffer)
         st = ms.stats()
         h2d, d2h = st.h2d_bytes, st.d2h_bytes
         phases.update(h2d_ms=st.h2d_ms, pack_ms=st.pack_ms, kernel_ms=st.kernel_ms, d2h_ms=st.d2h_ms,

@@ -82,6 +82,9 @@ struct gm_ctx {
 	size_t wl_cap;        // entries
 	int64_t seg_nt;       // nucleotides per prefilter/dfs launch pair
 	std::vector<uint32_t> hits;    // sorted, host
+	uint32_t *h_raw;               // pinned staging for the device -> host gather
+	size_t h_raw_cap;              // words
+	std::vector<uint64_t> keys;    // sort keys, reused
 	size_t n_hits;
 	gm_scan_stats_t stats;
 	// pending launch
@@ -572,6 +575,8 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->d_hits = NULL;
 	c->d_wl = NULL;
 	c->wl_cap = 0;
+	c->h_raw = NULL;
+	c->h_raw_cap = 0;
 	c->seg_nt = (int64_t)16 << 20;
 	c->use_split = false;
 	c->chars_cap = c->packed_cap = c->rec_cap = 0;
@@ -667,6 +672,7 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 	cudaFree(c->d_counters);
 	cudaFree(c->d_hits);
 	cudaFree(c->d_wl);
+	cudaFreeHost(c->h_raw);
 	for (int i = 0; i < 6; i++)
 		if (c->ev[i])
 			cudaEventDestroy(c->ev[i]);
@@ -987,26 +993,35 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	}
 	const size_t n = (size_t)cnt[1];
 	const size_t sw = (size_t)c->stride_words;
-	std::vector<uint32_t> raw(n * sw);
+	if (n * sw > c->h_raw_cap) {
+		cudaFreeHost(c->h_raw);
+		c->h_raw = NULL;
+		c->h_raw_cap = 0;
+		const size_t want = n * sw + n * sw / 4 + 4096;
+		CU(cudaMallocHost(&c->h_raw, want * 4));
+		c->h_raw_cap = want;
+	}
+	const uint32_t *raw = c->h_raw;
 	auto t0 = std::chrono::steady_clock::now();
 	if (n > 0)
-		CU(cudaMemcpy(raw.data(), c->d_hits, n * sw * 4, cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(c->h_raw, c->d_hits, n * sw * 4, cudaMemcpyDeviceToHost));
 	auto t1 = std::chrono::steady_clock::now();
-	// enumeration order: record, strand, start, DFS rank
-	std::vector<HitKey> keys(n);
+	// enumeration order: record, strand, start, DFS rank.  Two 64-bit keys per
+	// hit: (rec, comp, szero) and (seq, index into the gathered array)
+	std::vector<uint64_t> &keys = c->keys;
+	keys.resize(2 * n);
 	for (size_t i = 0; i < n; i++) {
 		const uint32_t *h = &raw[i * sw];
-		keys[i] = HitKey{h[0], h[3] & 0xff, h[1], h[2], (uint32_t)i};
+		keys[2 * i] = ((uint64_t)h[0] << 32) | ((uint64_t)(h[3] & 1) << 31) | (uint64_t)(h[1] & 0x7fffffffu);
+		keys[2 * i + 1] = ((uint64_t)h[2] << 32) | (uint64_t)i;
 	}
-	std::sort(keys.begin(), keys.end(), [](const HitKey &a, const HitKey &b) {
-		if (a.rec != b.rec) return a.rec < b.rec;
-		if (a.comp != b.comp) return a.comp < b.comp;
-		if (a.szero != b.szero) return a.szero < b.szero;
-		return a.seq < b.seq;
-	});
-	c->hits.resize(n * sw);
+	struct K2 { uint64_t a, b; };
+	K2 *kp = reinterpret_cast<K2 *>(keys.data());
+	std::sort(kp, kp + n, [](const K2 &x, const K2 &y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+	if (c->hits.size() < n * sw)
+		c->hits.resize(n * sw + n * sw / 4);
 	for (size_t i = 0; i < n; i++)
-		memcpy(&c->hits[i * sw], &raw[(size_t)keys[i].idx * sw], sw * 4);
+		memcpy(&c->hits[i * sw], &raw[(size_t)(uint32_t)kp[i].b * sw], sw * 4);
 	auto t2 = std::chrono::steady_clock::now();
 	c->n_hits = n;
 	c->stats.d2h_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();

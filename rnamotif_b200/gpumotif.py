@@ -152,13 +152,15 @@ class MotifSearch:
     def total_nt(self) -> int:
         return int(lib().gm_db_total_nt(self._ctx))
 
-    def scan(self, g_begin: int = 0, g_end: int | None = None, strands: int | None = None):
+    def scan(self, g_begin: int = 0, g_end: int | None = None, strands: int | None = None, copy: bool = True):
+        """gm_scan.  Returns the candidates (a copy; with copy=False a view of the
+        library's host buffer that is valid until the next scan)."""
         if g_end is None:
             g_end = self.total_nt
         if strands is None:
             strands = 2 if self.chk_both_strs else 1
         self._ck(lib().gm_scan(self._ctx, g_begin, g_end, strands), "gm_scan")
-        return self.hits()
+        return self.hits(copy)
 
     def scan_launch(self, g_begin: int = 0, g_end: int | None = None, strands: int | None = None):
         if g_end is None:
@@ -170,7 +172,7 @@ class MotifSearch:
     def scan_finish(self):
         self._ck(lib().gm_scan_finish(self._ctx), "gm_scan_finish")
 
-    def hits(self):
+    def hits(self, copy: bool = True):
         p, n, st = C.c_void_p(), C.c_size_t(), C.c_size_t()
         self._ck(lib().gm_hits(self._ctx, C.byref(p), C.byref(n), C.byref(st)), "gm_hits")
         dt = hit_dtype(self.n_descr)
@@ -178,7 +180,8 @@ class MotifSearch:
         if n.value == 0:
             return np.zeros(0, dtype=dt)
         buf = (C.c_uint8 * (n.value * st.value)).from_address(p.value)
-        return np.frombuffer(buf, dtype=dt).copy()
+        a = np.frombuffer(buf, dtype=dt)
+        return a.copy() if copy else a
 
     def stats(self) -> ScanStats:
         s = ScanStats()
