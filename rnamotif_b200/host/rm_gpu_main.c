@@ -8,8 +8,11 @@
  *     gm_db_upload_chars + gm_scan          (libgpumotif, include/gpumotif.h)
  *     for every candidate, in enumeration order: GM_replay_hit (rm_replay.c)
  *
- * Environment: GPUMOTIF_DEVICE (default 0), GPUMOTIF_BATCH_NT (default 64 M),
- * GPUMOTIF_STATS=1 prints per-batch timings to stderr.
+ * Environment: GPUMOTIF_DEVICES ("0,1,..": the batch is cut into that many
+ * ranges of start positions, one GPU each, no exchange; default GPUMOTIF_DEVICE
+ * or 0), GPUMOTIF_BATCH_NT (default 64 M), GPUMOTIF_STATS=1 prints per-batch
+ * timings to stderr.  This in-process sharding stands in for the MPI file farm of
+ * src/mrnamotif.c:105-192.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -57,6 +60,22 @@ static void revcomp_into(const char *src, int slen, char *dst)
 	dst[slen] = '\0';
 }
 
+#define MAX_GPUS 16
+
+/* enumeration order of the reference: record, strand, start, DFS rank */
+static size_t hit_stride;
+static int hit_cmp(const void *pa, const void *pb)
+{
+	const gm_hit_hdr_t *a = *(const gm_hit_hdr_t *const *)pa, *b = *(const gm_hit_hdr_t *const *)pb;
+	if (a->rec != b->rec)
+		return a->rec < b->rec ? -1 : 1;
+	if (a->comp != b->comp)
+		return a->comp < b->comp ? -1 : 1;
+	if (a->szero != b->szero)
+		return a->szero < b->szero ? -1 : 1;
+	return a->seq < b->seq ? -1 : a->seq > b->seq;
+}
+
 static void die_gm(const char *what)
 {
 	fprintf(stderr, "rnamotif_gpu: %s: %s\n", what, gm_last_error());
@@ -68,9 +87,12 @@ int main(int argc, char *argv[])
 	static gm_plan_t plan;
 	static char sid[SID_SIZE], sdef[SDEF_SIZE];
 	char err[512];
-	gm_ctx *ctx = NULL;
+	gm_ctx *ctxs[MAX_GPUS];
+	int devices[MAX_GPUS], n_gpus = 0, g;
+	const gm_hit_hdr_t **order = NULL;
+	size_t order_cap = 0;
 	IDENT_T *ip;
-	int chk_both_strs, show_progress, ecnt = 0, device = 0, stats = 0, eof = 0;
+	int chk_both_strs, show_progress, ecnt = 0, stats = 0, eof = 0;
 	int (*fgetseq)(FILE *, char *, int, char *, int, char *);
 	int64_t batch_nt = 64ll << 20, buf_cap, used;
 	char *buf, *rcbuf = NULL;
@@ -85,14 +107,22 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "rnamotif_gpu: descriptor cannot run on the device: %s\n", err);
 		exit(1);
 	}
-	if ((ev = getenv("GPUMOTIF_DEVICE")) != NULL)
-		device = atoi(ev);
+	if ((ev = getenv("GPUMOTIF_DEVICES")) != NULL && *ev) {
+		char *copy = strdup(ev), *tok;
+		for (tok = strtok(copy, ","); tok != NULL && n_gpus < MAX_GPUS; tok = strtok(NULL, ","))
+			devices[n_gpus++] = atoi(tok);
+		free(copy);
+	}
+	if (n_gpus == 0) {
+		devices[n_gpus++] = (ev = getenv("GPUMOTIF_DEVICE")) != NULL ? atoi(ev) : 0;
+	}
 	if ((ev = getenv("GPUMOTIF_BATCH_NT")) != NULL && atoll(ev) > 0)
 		batch_nt = atoll(ev);
 	if ((ev = getenv("GPUMOTIF_STATS")) != NULL)
 		stats = atoi(ev);
-	if (gm_ctx_create(&ctx, &plan, device))
-		die_gm("gm_ctx_create");
+	for (g = 0; g < n_gpus; g++)
+		if (gm_ctx_create(&ctxs[g], &plan, devices[g]))
+			die_gm("gm_ctx_create");
 
 	ip = RM_find_id("chk_both_strs");
 	chk_both_strs = ip == NULL ? 1 : ip->i_val.v_value.v_ival;
@@ -129,8 +159,7 @@ int main(int argc, char *argv[])
 	RM_setprog(P_MAIN);
 
 	while (!eof) {
-		const void *hits;
-		size_t n_hits, stride, h;
+		size_t n_hits = 0, stride = 0, h;
 		int r;
 
 		/* ---- read a batch ---- */
@@ -173,25 +202,49 @@ int main(int argc, char *argv[])
 			offs[r] = recs[r].off;
 		offs[n_recs] = used;
 
-		/* ---- search on the device ---- */
-		if (gm_db_upload_chars(ctx, buf, offs, n_recs))
-			die_gm("gm_db_upload_chars");
-		if (gm_scan(ctx, 0, used, chk_both_strs ? 2 : 1))
-			die_gm("gm_scan");
-		if (gm_hits(ctx, &hits, &n_hits, &stride))
-			die_gm("gm_hits");
-		if (stats) {
-			gm_scan_stats_t st;
-			gm_stats(ctx, &st);
-			fprintf(stderr, "rnamotif_gpu: batch %d records %lld nt: h2d %.2f ms pack %.2f ms kernel %.2f ms "
-				"d2h %.2f ms sort %.2f ms, %llu candidates, %u retries\n", n_recs, (long long)used,
-				st.h2d_ms, st.pack_ms, st.kernel_ms, st.d2h_ms, st.sort_ms,
-				(unsigned long long)st.n_hits, st.n_retries);
+		/* ---- search on the device(s): GPU g owns the starts in [g, g+1) * used / n_gpus ---- */
+		for (g = 0; g < n_gpus; g++)
+			if (gm_db_upload_chars(ctxs[g], buf, offs, n_recs))
+				die_gm("gm_db_upload_chars");
+		for (g = 0; g < n_gpus; g++)
+			if (gm_scan_launch(ctxs[g], used * g / n_gpus, used * (g + 1) / n_gpus, chk_both_strs ? 2 : 1))
+				die_gm("gm_scan_launch");
+		for (g = 0; g < n_gpus; g++) {
+			const void *hp;
+			size_t n, i;
+			if (gm_scan_finish(ctxs[g]))
+				die_gm("gm_scan_finish");
+			if (gm_hits(ctxs[g], &hp, &n, &stride))
+				die_gm("gm_hits");
+			if (n_hits + n > order_cap) {
+				order_cap = 2 * (n_hits + n) + 1024;
+				order = realloc(order, order_cap * sizeof *order);
+				if (order == NULL) {
+					fprintf(stderr, "rnamotif_gpu: out of memory\n");
+					exit(1);
+				}
+			}
+			for (i = 0; i < n; i++)
+				order[n_hits + i] = (const gm_hit_hdr_t *)((const char *)hp + i * stride);
+			n_hits += n;
+			if (stats) {
+				gm_scan_stats_t st;
+				gm_stats(ctxs[g], &st);
+				fprintf(stderr, "rnamotif_gpu: gpu %d batch %d records %lld nt: upload %.2f ms kernel %.2f ms "
+					"d2h %.2f ms sort %.2f ms, %llu candidates, %u retries\n", devices[g], n_recs,
+					(long long)used, st.h2d_ms, st.kernel_ms, st.d2h_ms, st.sort_ms,
+					(unsigned long long)st.n_hits, st.n_retries);
+			}
 		}
+		/* each GPU's list is sorted; with several GPUs merge them into one order
+		 * (the score program is stateful: src/score.c HOLD/RELEASE) */
+		hit_stride = stride;
+		if (n_gpus > 1 && n_hits > 1)
+			qsort(order, n_hits, sizeof *order, hit_cmp);
 
 		/* ---- replay the sink's tail in enumeration order ---- */
 		for (h = 0; h < n_hits;) {
-			const gm_hit_hdr_t *hdr = (const gm_hit_hdr_t *)((const char *)hits + h * stride);
+			const gm_hit_hdr_t *hdr = order[h];
 			const uint32_t rec = hdr->rec;
 			const int comp = hdr->comp;
 			REC_T *rp = &recs[rec];
@@ -212,7 +265,7 @@ int main(int argc, char *argv[])
 			} else
 				GM_replay_strand(rp->sid, rp->sdef, 0, rp->slen, sb);
 			for (; h < n_hits; h++) {
-				hdr = (const gm_hit_hdr_t *)((const char *)hits + h * stride);
+				hdr = order[h];
 				if (hdr->rec != rec || hdr->comp != comp)
 					break;
 				GM_replay_hit(hdr, (const gm_hit_el_t *)(hdr + 1));
@@ -227,6 +280,7 @@ int main(int argc, char *argv[])
 
 	RM_setprog(P_END);
 	RM_score(0, 0, NULL, NULL);
-	gm_ctx_destroy(ctx);
+	for (g = 0; g < n_gpus; g++)
+		gm_ctx_destroy(ctxs[g]);
 	exit(0);
 }

@@ -50,3 +50,16 @@ def test_stdout_equals_reference_binary_small_batches(name):
     out = run(GPU_BIN, name, {"GPUMOTIF_BATCH_NT": "300000"})
     ref = run(REF_BIN, name)
     assert out == ref
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref or rnamotif_gpu not built")
+@pytest.mark.parametrize("name", ["trna", "getbest", "pk1.strict"])
+def test_stdout_with_sharded_scan(name):
+    """The host driver's in-process sharding (GPUMOTIF_DEVICES): the batch is cut
+    into ranges of start positions, one context each, and the candidate lists are
+    merged before the (stateful) score replay.  Two contexts on device 0 exercise
+    the same code as two GPUs; with more than one GPU visible use them."""
+    import torch
+    devs = "0,1,0" if torch.cuda.device_count() > 1 else "0,0,0"
+    out = run(GPU_BIN, name, {"GPUMOTIF_DEVICES": devs, "GPUMOTIF_BATCH_NT": "1000000"})
+    assert hashlib.md5(out).hexdigest() == MD5[name]["md5"]
