@@ -276,8 +276,15 @@ def run_gpu_arm(args):
         # once for both strands (0.5 B per nt) + the candidates written
         alg_bytes = total * 0.5 + hits_n * (32 + 8 * ms.n_descr)
         achieved = alg_bytes / (k_ms / 1e3) / 1e9
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tj):
+            t = json.load(open(tj))
+            if t["workload"] == {"descr": args.descr, "mnt": args.mnt}:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]  # bytes per launch, ncu
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": which,
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                "peak_source": which,
                 "kernel": "gm_search_kernel", "kernel_ms": k_ms,
                 "note": "the search is integer-issue bound, not HBM bound (SURVEY.md F8); see issue"}
         line = {
