@@ -71,6 +71,21 @@ def run_one(name, descr_path, flags, fasta, out_plans, out_cands):
                 "stdout_md5": hashlib.md5(r.stdout).hexdigest()}
 
 
+def extras(fasta, out_plans, out_cands):
+    """Purpose-written descriptors (tests/golden/extra_descr/, ours) for corners no
+    shipped descriptor reaches; slack and strict."""
+    edir = os.path.join(HERE, "extra_descr")
+    out = []
+    for f in sorted(os.listdir(edir)):
+        if not f.endswith(".descr"):
+            continue
+        out.append(run_one("extra." + f[:-6], os.path.join(edir, f), [], fasta, out_plans, out_cands))
+        print(out[-1], flush=True)
+        out.append(run_one("extra." + f[:-6] + ".strict", os.path.join(edir, f), STRICT, fasta, out_plans, out_cands))
+        print(out[-1], flush=True)
+    return out
+
+
 def main():
     out_plans = os.path.join(HERE, "plans")
     out_cands = os.path.join(HERE, "cands")
@@ -81,6 +96,14 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         fasta = os.path.join(tmp, "golden.fastn")
         synth.write_fastn(fasta, ids, seq, off)
+        if "--extra-only" in sys.argv:
+            old = json.load(open(os.path.join(HERE, "manifest.json")))
+            manifest = [e for e in old["entries"] if not e["name"].startswith("extra.")]
+            manifest += extras(fasta, out_plans, out_cands)
+            json.dump({"db": "rnamotif_b200.synth.golden_db()", "total_nt": int(off[-1]), "entries": manifest},
+                      open(os.path.join(HERE, "manifest.json"), "w"), indent=1)
+            return
+        manifest += extras(fasta, out_plans, out_cands)
         tdir = os.path.join(REF, "data", "test")
         for t in TESTS:
             manifest.append(run_one(t, os.path.join(tdir, t + ".descr"), [], fasta, out_plans, out_cands))
