@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define GM_PLAN_MAGIC   0x474d504cu /* "GMPL" */
-#define GM_PLAN_VERSION 3
+#define GM_PLAN_VERSION 4
 
 #define GM_UNDEF      (-1)
 #define GM_UNBOUNDED  0x7fffffff
@@ -146,6 +146,19 @@ typedef struct gm_ctxel {
 	int32_t regex;               /* -1 if no seq= */
 } gm_ctxel_t;
 
+/* The reference's literal prefilter (optimize_query, src/compile.c:3315-3392;
+ * used by adjust_szero, src/find_motif.c:209-243): the best literal of any
+ * seq=, and how far from the start of the motif it can begin.  A start offset
+ * can only lead to a candidate if the literal occurs (within its mismatch
+ * allowance) at start + d for some d in [lmin, lmax].  Output-neutral. */
+typedef struct gm_literal {
+	int32_t present;             /* rm_o_stp != NULL */
+	int32_t regex;               /* the literal sub-pattern (rm_o_expbuf) as a fixed-length gm_regex_t */
+	int32_t lmin, lmax;          /* s_bestpat.b_lminlen / b_lmaxlen of rm_o_stp */
+	int32_t mismatch;            /* rm_o_stp->s_mismatch */
+	int32_t pad[3];
+} gm_literal_t;
+
 typedef struct gm_plan {
 	uint32_t magic, version;
 	int32_t n_descr;             /* rm_n_descr */
@@ -159,6 +172,7 @@ typedef struct gm_plan {
 	                                     s_forward is always searches[s+1]
 	                                     (src/compile.c:3290-3296) */
 	gm_ctxel_t lctx, rctx;
+	gm_literal_t literal;
 	gm_elem_t    elems[GM_MAX_DESCR];
 	gm_site_t    sites[GM_MAX_SITES];
 	gm_pairset_t pairsets[GM_MAX_PAIRSET];

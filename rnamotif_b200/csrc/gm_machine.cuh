@@ -197,12 +197,14 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	// by the block, then one private region per warp, then the lane state
 	const int nwarps = nt >> 5;
 	const size_t pb_bytes = (((size_t)2 * n_dups * 4 * nwb * 4) + 15) & ~(size_t)15;
-	const size_t buf_bytes = 2 * (size_t)Lbytes + pb_bytes + (GM_REC_CACHE + 2) * 8;
+	const size_t lit_bytes = c_par.lit_present ? (((size_t)2 * nwb * 4) + 15) & ~(size_t)15 : 0;
+	const size_t buf_bytes = 2 * (size_t)Lbytes + pb_bytes + (GM_REC_CACHE + 2) * 8 + lit_bytes;
 	const size_t warp_bytes = 16 + (size_t)stage_bytes + NBUF * buf_bytes + GM_QCAP * 2;
 	uint8_t *p = smem_raw;
 	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
 	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
 	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
+	uint64_t *sm_litB = reinterpret_cast<uint64_t *>(p);       p += 16 * 8; // literal prefilter class masks
 	uint8_t *wp = p + (size_t)warp * warp_bytes;               p += (size_t)nwarps * warp_bytes;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
 	WarpTile *sm = reinterpret_cast<WarpTile *>(wp);           wp += 16;
@@ -217,6 +219,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		reinterpret_cast<uint32_t *>(sm_ps)[i] = reinterpret_cast<const uint32_t *>(c_plan.pairsets)[i];
 	for (int i = tid; i < ND; i += nt)
 		sm_elmm[i] = pk16(c_plan.elems[i].minlen, c_plan.elems[i].maxlen);
+	if (tid < 16)
+		sm_litB[tid] = c_par.lit_present ? c_plan.regex[c_par.lit_rx].B[tid] : 0;
 	if (lane == 0)
 		mbar_init(&sm->bar, 1);
 
@@ -255,6 +259,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	pb.base = reinterpret_cast<uint32_t *>(bufs);
 	pb.nwb = nwb;
 	pb.n_dups = n_dups;
+	uint32_t *sm_lit = reinterpret_cast<uint32_t *>(bufs); // literal-occurrence bitsets [strand][nwb]
 	bool one_rec = false;
 	int r_lo = 0;
 	int64_t rec0_off = 0;
@@ -274,6 +279,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		sm_rc = bp + Lbytes;
 		pb.base = reinterpret_cast<uint32_t *>(bp + 2 * (size_t)Lbytes);
 		sm_rec = reinterpret_cast<int64_t *>(bp + 2 * (size_t)Lbytes + pb_bytes);
+		sm_lit = reinterpret_cast<uint32_t *>(bp + 2 * (size_t)Lbytes + pb_bytes + (GM_REC_CACHE + 2) * 8);
 		gA = A.g_begin + t * (int64_t)TILE;
 		gB = min(gA + (int64_t)TILE, A.g_end);
 		lo = gA - H;
@@ -334,6 +340,33 @@ __global__ void gm_search_kernel(const ScanArgs A)
 						pbw[((size_t)(0 * n_dups + dd) * 4 + x) * nwb + w] = bf;
 						pbw[((size_t)(1 * n_dups + dd) * 4 + x) * nwb + w] = br;
 					}
+				}
+			}
+		}
+		if (c_par.lit_present) {
+			// literal prefilter (adjust_szero, src/find_motif.c:209-243): bit i of a
+			// strand's set = the best literal occurs at tile position i within its
+			// mismatch allowance (mm_advance on fixed-length items, src/mm_regexp.c:369-469)
+			const int len = c_par.lit_len, l_mm = c_par.lit_mm;
+			const uint64_t dot = c_plan.regex[c_par.lit_rx].dot;
+			for (int w = 0; w < nwb; w++) {
+				const int i = w * 32 + lane;
+				bool mf = i + len <= Lbytes, mr = mf;
+				int cf = 0, cr = 0;
+				for (int k = 0; k < len && (mf || mr); k++) {
+					const uint64_t bit = (uint64_t)1 << k;
+					if (dot & bit)
+						continue;
+					if (mf && !(sm_litB[icode_of(sm_fwd[i + k])] & bit) && ++cf > l_mm)
+						mf = false;
+					if (mr && !(sm_litB[icode_of(sm_rc[i + k])] & bit) && ++cr > l_mm)
+						mr = false;
+				}
+				const unsigned bf = __ballot_sync(0xffffffffu, mf);
+				const unsigned br = __ballot_sync(0xffffffffu, mr);
+				if (lane == 0) {
+					sm_lit[w] = bf;
+					sm_lit[nwb + w] = br;
 				}
 			}
 		}
@@ -414,6 +447,21 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
 		const int base = comp ? Lbytes - 1 - idx : idx;
 		const int dl = min(W, slen - szero) - 1;
+		if (c_par.lit_present) {
+			// the literal must begin lmin..lmax nucleotides after the start and end
+			// inside the window
+			const int l = c_par.lit_lmin;
+			int h = min(c_par.lit_lmax, dl + 1 - c_par.lit_len);
+			bool any = false;
+			const uint32_t *set = sm_lit + comp * nwb;
+			for (; h >= l && !any; h -= 64) {
+				const int l0 = max(l, h - 63), n = h - l0 + 1;
+				const uint64_t ones = n >= 64 ? ~0ull : ((1ull << n) - 1);
+				any = (bits64(set, base + l0) & ones) != 0;
+			}
+			if (!any)
+				return false;
+		}
 		if (c_par.pf_search >= 0) {
 			// any span end at all for the first helix of the descriptor?  (It is
 			// search 0, or follows fixed-length single strands, so its 5' start

@@ -72,6 +72,8 @@ struct DevParams {
 	int refill_min;         // idle lanes a warp waits for before it hands out new starts
 	int pf_search;          // search whose candidate mask is the level-0 prefilter, or -1
 	int pf_z;               // its 5' start relative to the window (fixed-length ss before it)
+	int lit_present;        // literal prefilter (gm_plan_t::literal): regex index, window, length
+	int lit_rx, lit_lmin, lit_lmax, lit_mm, lit_len;
 	int lite;               // plan of single strands and proper helices only: the lane
 	                        // state has no per-element counter words; the sink reads the
 	                        // mispair / mismatch counts from the frames through elsrc[]

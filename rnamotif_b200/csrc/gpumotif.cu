@@ -370,6 +370,18 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 			break;
 		}
 	}
+	// literal prefilter
+	par->lit_present = 0;
+	if (pl->literal.present && pl->literal.regex >= 0 && pl->literal.regex < pl->n_regex &&
+	    pl->literal.lmax >= pl->literal.lmin && pl->literal.lmin >= 0 &&
+	    pl->regex[pl->literal.regex].mm_len > 0 && getenv("GPUMOTIF_NO_LITERAL") == NULL) {
+		par->lit_present = 1;
+		par->lit_rx = pl->literal.regex;
+		par->lit_lmin = pl->literal.lmin;
+		par->lit_lmax = pl->literal.lmax;
+		par->lit_mm = pl->literal.mismatch;
+		par->lit_len = pl->regex[pl->literal.regex].mm_len;
+	}
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
 		if (ds[s].kind != K_SS && ds[s].kind != K_WC)
@@ -410,12 +422,14 @@ static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state 
 	const int Lb = (tile + 2 * c->par.halo + 15) & ~15;
 	const size_t stage = ((Lb >> 1) + 32 + 15) & ~15;
 	const size_t pb = (((size_t)2 * c->par.n_dups * 4 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15;
-	const size_t buf_bytes = 2 * (size_t)Lb + pb + (GM_REC_CACHE + 2) * 8;
+	const size_t lit = c->par.lit_present ? (((size_t)2 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15 : 0;
+	const size_t buf_bytes = 2 * (size_t)Lb + pb + (GM_REC_CACHE + 2) * 8 + lit;
 	const size_t warp_bytes = 16 + stage + (with_state ? 2 : 1) * buf_bytes + GM_QCAP * 2;
 	size_t n = 0;
 	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
 	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
 	n += (c->par.n_descr * 4 + 15) & ~15;
+	n += 16 * 8;
 	n += (size_t)(threads >> 5) * warp_bytes;
 	if (with_state)
 		n += (size_t)c->par.words_per_lane * threads * 4;
@@ -513,7 +527,7 @@ static int configure_launch(gm_ctx *c, int tile)
 	c->par.win_stride = words * 4;
 	c->par.win_stage = (((wtot + 1) / 2 + 1 + 15 + 15) & ~15);
 	bool eligible = wtot <= 512 &&
-		(c->par.pf_search >= 0 ||
+		(c->par.pf_search >= 0 || c->par.lit_present ||
 		 (S0.rx5 >= 0 && S0.mm5 == 0 && !c->plan.regex[S0.rx5].eol));
 	// The fused kernel is the default: on the measured configurations it is the
 	// faster of the two (profiles/README.md).  GPUMOTIF_PATH=split selects the

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPUMOTIF_LIB") or os.path.join(_HERE, "csrc", "libgpumotif.so")
 
-PLAN_BYTES = 32120
+PLAN_BYTES = 32152
 
 
 class ScanStats(C.Structure):

@@ -29,6 +29,8 @@ extern int rm_n_searches;
 extern SITE_T *rm_sites;
 extern STREL_T *rm_lctx, *rm_rctx;
 extern ARGS_T *rm_args;
+extern STREL_T *rm_o_stp;
+extern char *rm_o_expbuf;
 
 /* regexp bytecodes, src/regexp.c:74-88 */
 #define RX_CBRA 2
@@ -148,13 +150,20 @@ static int add_pos(gm_regex_t *rx, uint16_t cls, int skip, int star, int dot)
 }
 
 /* s_expbuf -> gm_regex_t.  Bytecode layout: src/regexp.c:158-385. */
+static int flatten_expbuf(const char *expbuf, int bol, int mismatch, gm_regex_t *rx, const char *what);
+
 static int flatten_regex(STREL_T *stp, gm_regex_t *rx, const char *what)
 {
-	const unsigned char *ep = (const unsigned char *)stp->s_expbuf;
+	return flatten_expbuf(stp->s_expbuf, stp->s_seq[0] == '^', stp->s_mismatch, rx, what);
+}
+
+static int flatten_expbuf(const char *expbuf, int bol, int mismatch, gm_regex_t *rx, const char *what)
+{
+	const unsigned char *ep = (const unsigned char *)expbuf;
 	int i, run, maxrun;
 
 	memset(rx, 0, sizeof *rx);
-	rx->bol = stp->s_seq[0] == '^';
+	rx->bol = bol;
 	rx->mm_len = -1;
 	for (;;) {
 		gm_re_item_t it;
@@ -227,7 +236,7 @@ static int flatten_regex(STREL_T *stp, gm_regex_t *rx, const char *what)
 			run = 0;
 	}
 	rx->closure_iters = maxrun;
-	if (stp->s_mismatch > 0) {
+	if (mismatch > 0) {
 		/* mm_seqlen's mmok (src/mm_regexp.c:51-193) already refused
 		 * anything that is not fixed-length */
 		if (rx->skip != 0)
@@ -464,6 +473,26 @@ int gm_flatten_plan(gm_plan_t *pl, char *errbuf, size_t errlen)
 			gs->pos[k].l2r = pp->p_addr.a_l2r;
 			gs->pos[k].offset = pp->p_addr.a_offset;
 		}
+	}
+
+	/* the literal prefilter, if the front end chose one (-O, default 2.5) */
+	memset(&pl->literal, 0, sizeof pl->literal);
+	pl->literal.regex = -1;
+	if (rm_o_stp != NULL && rm_o_expbuf != NULL && rm_o_stp->s_bestpat.b_lmaxlen != UNBOUNDED &&
+	    pl->n_regex < GM_MAX_REGEX) {
+		gm_regex_t *rx = &pl->regex[pl->n_regex];
+		/* literals are runs of single characters / classes; anything else just
+		 * means no prefilter (it is an optimisation, never an error) */
+		if (flatten_expbuf(rm_o_expbuf, 0, 1, rx, "best literal") == 0 && rx->npos > 0 && rx->skip == 0 &&
+		    !rx->eol) {
+			rx->mm_len = rx->npos;
+			pl->literal.present = 1;
+			pl->literal.regex = pl->n_regex++;
+			pl->literal.lmin = rm_o_stp->s_bestpat.b_lminlen;
+			pl->literal.lmax = rm_o_stp->s_bestpat.b_lmaxlen;
+			pl->literal.mismatch = rm_o_stp->s_mismatch;
+		} else if (errbuf != NULL && errlen > 0)
+			errbuf[0] = '\0';
 	}
 
 	if (flatten_ctx(pl, rm_lctx, &pl->lctx, "left ctx"))
