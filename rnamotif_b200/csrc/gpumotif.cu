@@ -998,6 +998,10 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 		if (cnt[1] <= c->hit_cap)
 			break;
 		// the hit buffer was too small: nothing is lost, run again with room
+		if ((double)cnt[1] * c->stride_words * 4 > 48e9)
+			return fail("%llu candidates in this range need %.1f GB of hit buffer: scan a smaller range "
+				    "(gm_scan(ctx, lo, hi, ...)) or tighten the descriptor",
+				    cnt[1], (double)cnt[1] * c->stride_words * 4 / 1e9);
 		c->stats.n_retries++;
 		cudaFree(c->d_hits);
 		c->d_hits = NULL;
