@@ -367,6 +367,22 @@ __device__ __forceinline__ int chk_seq5(Lane &L, const DevSearch &S, int off, in
 	return rx_match(rx, L.sq + off, len);
 }
 
+// chk_seq on helix strand d, src/find_motif.c:1810-1824.  With mismatch= the
+// count that mm_step leaves in s_n_mismatches -- on success AND on failure --
+// goes to the element's counter word, which is what the sink reports.
+__device__ __noinline__ int chk_seq_el(Lane &L, int d, int off, int len)
+{
+	const gm_elem_t &e = c_plan.elems[d];
+	const gm_regex_t &rx = c_plan.regex[e.regex];
+	if (e.mismatch > 0) {
+		int n_mm;
+		const int ok = rx_match_mm(rx, L.sq + off, len, e.mismatch, &n_mm);
+		L_EM(L, d) = pk16(lo16(L_EM(L, d)), n_mm);
+		return ok;
+	}
+	return rx_match(rx, L.sq + off, len);
+}
+
 // match_wchlx, src/find_motif.c:1008-1109, as a generator: advance the helix
 // (s5, s3) from its current length hl (0 = nothing tested yet) to the next
 // length that passes match_wchlx's own acceptance tests.  false = the
@@ -405,6 +421,58 @@ __device__ __forceinline__ bool wx_next(const Lane &L, const DevSearch &S, int s
 		hl++;
 		chk = true;
 	}
+}
+
+// The same for helices whose strands carry seq= with mismatch=.  match_wchlx
+// collects EVERY helix of (s5, s3) before find_wchlx / find_pknot3 / find_4plex
+// descend into the first one (src/find_motif.c:436-460), so the mismatch counts
+// a candidate reports are those of the LAST chk_seq calls of the whole
+// extension: wx_finish_mm runs the rest of it for that side effect.
+__device__ __noinline__ bool wx_next_mm(Lane &L, const DevSearch &S, int s5, int s3, int s3lim,
+	int *p_hl, int *p_mpr, int *p_lbpr)
+{
+	int hl = *p_hl, mpr = *p_mpr, lbpr = *p_lbpr;
+	bool chk = false, more = false;
+	if (hl == 0) {
+		if (paired(S.duplex, L.sq[s5], L.sq[s3])) {
+			hl = 1; mpr = 0; lbpr = 1;
+		} else if (!(S.ends & GM_5PAIRED)) {
+			hl = 1; mpr = 1; lbpr = 0;
+		} else
+			return false;
+		chk = true;
+	}
+	for (;;) {
+		if (chk) {
+			if (hl >= S.minlen &&
+			    !(!lbpr && (S.ends & GM_3PAIRED)) &&
+			    !(S.pfrac && mpr > c_plan.lentab[S.lentab + hl]) &&
+			    !(S.rx5 >= 0 && !chk_seq_el(L, S.d, s5, hl)) &&
+			    !(S.rx3 >= 0 && !chk_seq_el(L, S.d3, s3 - hl + 1, hl))) {
+				more = true;
+				break;
+			}
+		}
+		if (s3 - hl + 1 < s3lim || hl >= S.maxlen)
+			break;
+		if (paired(S.duplex, L.sq[s5 + hl], L.sq[s3 - hl]))
+			lbpr = 1;
+		else {
+			if (++mpr > S.mplim)
+				break;
+			lbpr = 0;
+		}
+		hl++;
+		chk = true;
+	}
+	*p_hl = hl; *p_mpr = mpr; *p_lbpr = lbpr;
+	return more;
+}
+__device__ __noinline__ void wx_finish_mm(Lane &L, const DevSearch &S, int s5, int s3, int s3lim,
+	int hl, int mpr, int lbpr)
+{
+	while (wx_next_mm(L, S, s5, s3, s3lim, &hl, &mpr, &lbpr))
+		;
 }
 
 // find_minlen / find_maxlen, src/find_motif.c:642-665
@@ -457,9 +525,9 @@ __device__ __noinline__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int
 			return false;
 		if (S.pfrac && mpr > c_plan.lentab[S.lentab + hl])
 			return false;
-		if (S.rx5 >= 0 && !rx_match(c_plan.regex[S.rx5], L.sq + s5, hl))
+		if (S.rx5 >= 0 && !chk_seq_el(L, S.d, s5, hl))
 			return false;
-		if (e3.regex >= 0 && !rx_match(c_plan.regex[e3.regex], L.sq + s3 - hl + 1, hl))
+		if (e3.regex >= 0 && !chk_seq_el(L, d3, s3 - hl + 1, hl))
 			return false;
 		*hlen = hl;
 		*n_mpr = mpr;
@@ -492,7 +560,7 @@ __device__ __noinline__ bool match_triplex(Lane &L, const DevSearch &S, int dd1,
 	}
 	if (!l_pr && (S.ends & GM_3PAIRED))
 		return false;
-	if (e1.regex >= 0 && !rx_match(c_plan.regex[e1.regex], L.sq + s2 - tlen + 1, tlen))
+	if (e1.regex >= 0 && !chk_seq_el(L, dd1, s2 - tlen + 1, tlen))
 		return false;
 	*n_mpr = mpr;
 	return true;
@@ -524,9 +592,9 @@ __device__ __noinline__ bool match_4plex(Lane &L, int dd1, int dd2, int s1, int 
 	}
 	if (!l_pr && (e1.ends & GM_3PAIRED))
 		return false;
-	if (e1.regex >= 0 && !rx_match(c_plan.regex[e1.regex], L.sq + s2, qlen))
+	if (e1.regex >= 0 && !chk_seq_el(L, dd1, s2, qlen))
 		return false;
-	if (e2.regex >= 0 && !rx_match(c_plan.regex[e2.regex], L.sq + s3 - qlen + 1, qlen))
+	if (e2.regex >= 0 && !chk_seq_el(L, dd2, s3 - qlen + 1, qlen))
 		return false;
 	*n_mpr = mpr;
 	return true;

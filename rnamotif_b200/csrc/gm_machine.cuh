@@ -179,7 +179,10 @@ __device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, i
 // helices only (most descriptors): the pseudoknot / parallel helix / triplex /
 // quadruplex code is left out, which keeps the hot loop inside the
 // instruction cache.
-template <int MODE, bool FULL>
+// LIT = true adds the literal prefilter (plans with a gm_plan_t::literal); a
+// template parameter so that plans without one run exactly the code they had
+// before it existed.
+template <int MODE, bool FULL, bool LIT>
 __global__ void gm_search_kernel(const ScanArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -197,14 +200,14 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	// by the block, then one private region per warp, then the lane state
 	const int nwarps = nt >> 5;
 	const size_t pb_bytes = (((size_t)2 * n_dups * 4 * nwb * 4) + 15) & ~(size_t)15;
-	const size_t lit_bytes = c_par.lit_present ? (((size_t)2 * nwb * 4) + 15) & ~(size_t)15 : 0;
+	const size_t lit_bytes = LIT ? (((size_t)2 * nwb * 4) + 15) & ~(size_t)15 : 0;
 	const size_t buf_bytes = 2 * (size_t)Lbytes + pb_bytes + (GM_REC_CACHE + 2) * 8 + lit_bytes;
 	const size_t warp_bytes = 16 + (size_t)stage_bytes + NBUF * buf_bytes + GM_QCAP * 2;
 	uint8_t *p = smem_raw;
 	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
 	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
 	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
-	uint64_t *sm_litB = reinterpret_cast<uint64_t *>(p);       p += 16 * 8; // literal prefilter class masks
+	uint64_t *sm_litB = reinterpret_cast<uint64_t *>(p);       p += LIT ? 16 * 8 : 0; // literal prefilter class masks
 	uint8_t *wp = p + (size_t)warp * warp_bytes;               p += (size_t)nwarps * warp_bytes;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
 	WarpTile *sm = reinterpret_cast<WarpTile *>(wp);           wp += 16;
@@ -219,8 +222,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		reinterpret_cast<uint32_t *>(sm_ps)[i] = reinterpret_cast<const uint32_t *>(c_plan.pairsets)[i];
 	for (int i = tid; i < ND; i += nt)
 		sm_elmm[i] = pk16(c_plan.elems[i].minlen, c_plan.elems[i].maxlen);
-	if (tid < 16)
-		sm_litB[tid] = c_par.lit_present ? c_plan.regex[c_par.lit_rx].B[tid] : 0;
+	if (LIT && tid < 16)
+		sm_litB[tid] = c_plan.regex[c_par.lit_rx].B[tid];
 	if (lane == 0)
 		mbar_init(&sm->bar, 1);
 
@@ -343,7 +346,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				}
 			}
 		}
-		if (c_par.lit_present) {
+		if (LIT) {
 			// literal prefilter (adjust_szero, src/find_motif.c:209-243): bit i of a
 			// strand's set = the best literal occurs at tile position i within its
 			// mismatch allowance (mm_advance on fixed-length items, src/mm_regexp.c:369-469)
@@ -447,7 +450,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
 		const int base = comp ? Lbytes - 1 - idx : idx;
 		const int dl = min(W, slen - szero) - 1;
-		if (c_par.lit_present) {
+		if (LIT) {
 			// the literal must begin lmin..lmax nucleotides after the start and end
 			// inside the window
 			const int l = c_par.lit_lmin;

@@ -41,7 +41,10 @@ struct DevSearch {
 	unsigned duplex;       // ps_mat[0] as 25 bits
 	int lentab;            // per-length pairfrac table (offset into plan.lentab) or -1
 	int rx5, rx3;          // regex of head / far strand, or -1
-	int mm5;               // mismatch limit of the head (ss only on the device)
+	int mm5;               // mismatch limit of the head (ss: used by the fused ss trip)
+	int hmm;               // helix: d or d3 has seq= with mismatch= (their counters need the
+	                       // whole extension of match_wchlx, see wx_finish_mm)
+	int pad0;
 	int last;              // 1 for the final search (hit sink follows)
 	int fr;                // word offset of this search's frame in the lane state
 	int dupi;              // index of `duplex` in DevParams::dups (pair bitsets), or -1
@@ -52,7 +55,7 @@ struct DevSearch {
 	int kid_t, kid_off;
 	int sib_t, sib_off;
 };
-static_assert(sizeof(DevSearch) == 27 * 4, "DevSearch is staged with an odd word stride");
+static_assert(sizeof(DevSearch) == 29 * 4, "DevSearch is staged with an odd word stride");
 
 #define GM_MAX_DUPS 8
 
@@ -189,13 +192,15 @@ __device__ __noinline__ int rx_match(const gm_regex_t &rx, const uint8_t *s, int
 
 // mm_step/mm_advance, src/mm_regexp.c:353-469 (fixed-length patterns).
 // Returns 1 and the mismatch count of the first (leftmost) placement that
-// stays within l_mm.
+// stays within l_mm; on failure *n_mm is what the last placement tried left
+// behind (mm_advance counts into the caller's s_n_mismatches as it goes).
 __device__ __noinline__ int rx_match_mm(const gm_regex_t &rx, const uint8_t *s, int n, int l_mm, int *n_mm)
 {
 	const int m = rx.mm_len;
 	const int last = rx.bol ? 0 : n;
+	int cnt = 0;
 	for (int p1 = 0; p1 <= last; p1++) {
-		int cnt = 0;
+		cnt = 0;
 		bool ok = true;
 		for (int k = 0; k < m; k++) {
 			if (p1 + k >= n) { ok = false; break; }
@@ -211,7 +216,7 @@ __device__ __noinline__ int rx_match_mm(const gm_regex_t &rx, const uint8_t *s, 
 			return 1;
 		}
 	}
-	*n_mm = 0;
+	*n_mm = cnt;
 	return 0;
 }
 

@@ -109,17 +109,19 @@ extern "C" int gm_device_count(void)
 // kernel variants: FULL only when the plan has something besides single strands
 // and proper helices
 typedef void (*search_kernel_t)(const ScanArgs);
-static search_kernel_t fused_kernel(bool full)
+static search_kernel_t fused_kernel(bool full, bool lit)
 {
-	return full ? (search_kernel_t)gm_search_kernel<0, true> : (search_kernel_t)gm_search_kernel<0, false>;
+	if (lit)
+		return full ? (search_kernel_t)gm_search_kernel<0, true, true> : (search_kernel_t)gm_search_kernel<0, false, true>;
+	return full ? (search_kernel_t)gm_search_kernel<0, true, false> : (search_kernel_t)gm_search_kernel<0, false, false>;
 }
 static search_kernel_t dfs_kernel(bool full)
 {
 	return full ? (search_kernel_t)gm_dfs_kernel<true> : (search_kernel_t)gm_dfs_kernel<false>;
 }
-static search_kernel_t pre_kernel(void)
+static search_kernel_t pre_kernel(bool lit)
 {
-	return (search_kernel_t)gm_search_kernel<1, false>;
+	return lit ? (search_kernel_t)gm_search_kernel<1, false, true> : (search_kernel_t)gm_search_kernel<1, false, false>;
 }
 
 // --------------------------------------------------------------- plan checks
@@ -173,8 +175,6 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 			return fail("element %d: length range [%d,%d] not supported", d, e.minlen, e.maxlen);
 		if (e.regex >= pl->n_regex || e.pairset >= pl->n_pairsets)
 			return fail("element %d: table index out of range", d);
-		if (e.type != GM_SS && e.regex >= 0 && e.mismatch > 0)
-			return fail("element %d: mismatch= on a helix strand is not supported on the device", d);
 		if (e.type != GM_SS && e.regex >= 0 && e.minlen == 0)
 			return fail("element %d: seq= on a helix with minlen=0 is undefined in the reference "
 				    "(src/find_motif.c:986-1021 reads an unset candidate)", d);
@@ -226,6 +226,8 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 					return fail("search %d: bad mate", s);
 			S.d3 = e.mates[need - 1];
 			S.rx3 = pl->elems[S.d3].regex;
+			S.hmm = (e.regex >= 0 && e.mismatch > 0) ||
+				(S.rx3 >= 0 && pl->elems[S.d3].mismatch > 0);
 			if (e.pairset < 0)
 				return fail("search %d: helix without a pairset", s);
 			if (S.pfrac && e.lentab < 0)
@@ -384,8 +386,8 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	}
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
-		if (ds[s].kind != K_SS && ds[s].kind != K_WC)
-			par->lite = 0;
+		if ((ds[s].kind != K_SS && ds[s].kind != K_WC) || ds[s].hmm)
+			par->lite = 0; // helix mismatch counts live in the per-element words
 	// batch size of the lane refill: large when the prefilter leaves short
 	// enumerations (the batch then runs in step), small when they are long
 	{
@@ -429,7 +431,7 @@ static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state 
 	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
 	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
 	n += (c->par.n_descr * 4 + 15) & ~15;
-	n += 16 * 8;
+	n += c->par.lit_present ? 16 * 8 : 0;
 	n += (size_t)(threads >> 5) * warp_bytes;
 	if (with_state)
 		n += (size_t)c->par.words_per_lane * threads * 4;
@@ -457,8 +459,8 @@ static int warps_per_sm(gm_ctx *c, int threads, int tile)
 	if (need + 1024 > 227 * 1024)
 		return 0;
 	int n = 0;
-	if (cudaFuncSetAttribute(fused_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
-	    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel(c->full), threads, need) != cudaSuccess) {
+	if (cudaFuncSetAttribute(fused_kernel(c->full, c->par.lit_present != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
+	    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel(c->full, c->par.lit_present != 0), threads, need) != cudaSuccess) {
 		cudaGetLastError();
 		return 0;
 	}
@@ -510,12 +512,15 @@ static int configure_launch(gm_ctx *c, int tile)
 	c->threads = best_t;
 	c->par.tile = tile;
 	c->smem_bytes = smem_need(c, best_t, tile);
-	CU(cudaFuncSetAttribute(fused_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+	CU(cudaFuncSetAttribute(fused_kernel(c->full, c->par.lit_present != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
 	int per_sm = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel(c->full), c->threads, c->smem_bytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel(c->full, c->par.lit_present != 0), c->threads, c->smem_bytes));
 	if (per_sm < 1)
 		return fail("search kernel does not fit on an SM (threads %d, smem %zu)", c->threads, c->smem_bytes);
 	c->blocks = per_sm * c->n_sm;
+	if (getenv("GPUMOTIF_DEBUG") != NULL)
+		fprintf(stderr, "gpumotif: tile %d, %d threads x %d blocks (%d per SM), %zu bytes smem per block, %s kernel\n",
+			tile, c->threads, c->blocks, per_sm, c->smem_bytes, c->full ? "full" : "lite");
 
 	// split path: the worklist kernels.  Eligible when search 0 has a prefilter
 	// worth a pass of its own and a lane window fits comfortably in shared memory.
@@ -561,9 +566,9 @@ static int configure_launch(gm_ctx *c, int tile)
 		cudaGetLastError();
 		int na = 0;
 		if (c->b_threads > 0 && c->a_smem <= smem_sm &&
-		    cudaFuncSetAttribute(pre_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
+		    cudaFuncSetAttribute(pre_kernel(c->par.lit_present != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
 		    cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->b_smem) == cudaSuccess &&
-		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(), c->a_threads, c->a_smem) == cudaSuccess &&
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(c->par.lit_present != 0), c->a_threads, c->a_smem) == cudaSuccess &&
 		    na >= 1) {
 			c->a_blocks = na * c->n_sm;
 			c->use_split = true;
@@ -900,7 +905,7 @@ static int launch(gm_ctx *c)
 			A.n_tiles = (hi - lo + c->par.tile - 1) / c->par.tile;
 			A.tile_counter = c->d_counters + 8 + i;
 			int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
-			fused_kernel(c->full)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+			fused_kernel(c->full, c->par.lit_present != 0)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 			CU(cudaGetLastError());
 			c->stats.n_launches++;
 			lo = hi;
@@ -909,7 +914,7 @@ static int launch(gm_ctx *c)
 		if (n_chunks > 0)
 			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
 		int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
-		fused_kernel(c->full)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+		fused_kernel(c->full, c->par.lit_present != 0)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 		CU(cudaGetLastError());
 		c->stats.n_launches++;
 	} else if (A.n_tiles > 0) {
@@ -934,7 +939,7 @@ static int launch(gm_ctx *c)
 			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
 			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
 			int ablocks = (int)std::min<int64_t>(c->a_blocks, A.n_tiles);
-			pre_kernel()<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
+			pre_kernel(c->par.lit_present != 0)<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
 			dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
 			CU(cudaGetLastError());

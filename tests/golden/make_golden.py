@@ -9,7 +9,12 @@ binaries built by `make -C oracle ref` and `make -C rnamotif_b200/host`):
                          binary (oracle/_ref/rnamotif_cand -O0) over
                          rnamotif_b200.synth.golden_db(): every assignment that
                          reaches the hit sink (src/find_motif.c:362-394), in
-                         enumeration order, with RM_score's verdict
+                         enumeration order, with RM_score's verdict.  The binary
+                         runs with oracle/_ref/malloc_ff.so preloaded: its
+                         -strict_helices checks read fm_window[] cells nothing has
+                         written yet (uninitialised malloc memory, oracle/malloc_ff.c);
+                         the shim makes them read UNDEF, so the stream depends on
+                         the input only
   manifest.json          names, flags, candidate counts, md5 of raw stdout
 
 Usage: python tests/golden/make_golden.py
@@ -48,6 +53,7 @@ def run_one(name, descr_path, flags, fasta, out_plans, out_cands):
             return {"name": name, "skipped": "plan: " + r.stderr.decode(errors="replace").strip().splitlines()[-1]}
         plan = open(env["GM_PLAN_OUT"], "rb").read()
         try:
+            env["LD_PRELOAD"] = os.path.join(REF, "malloc_ff.so")
             r = subprocess.run([os.path.join(REF, "rnamotif_cand"), "-O0", *flags, "-descr",
                                 os.path.basename(descr_path), fasta], cwd=d, env=env, capture_output=True,
                                timeout=300)
