@@ -87,6 +87,28 @@ int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n
  * pointer, e.g. torch tensor storage). */
 int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_t *rec_off, int n_rec);
 
+/* FN_fgetseq on the device (src/dbutil.c:42-128): `text` is FASTA exactly as it
+ * sits in the file(s) -- the bytes go host -> device as they are and the
+ * reader's work (header lines out, every isalpha character of the rest kept,
+ * records cut at every '>' outside a header) is done there, followed by the
+ * 4-bit pack.  The text must begin with '>' (:56-60).  The host never touches
+ * a sequence byte: the record table comes back through gm_db_records() and the
+ * characters a caller needs to print or score a candidate through
+ * gm_hit_windows().  Blocks until the record table is known; the pack runs
+ * on asynchronously like gm_db_upload_chars. */
+int gm_db_upload_fastn(gm_ctx *c, const char *text, size_t n_bytes);
+
+/* Record table of the uploaded batch: rec_off[0..n_rec] as in
+ * gm_db_upload_chars, and -- after gm_db_upload_fastn only, else NULL --
+ * hdr_off[r] = offset in `text` of record r's '>' (hdr_off[n_rec] = n_bytes), so
+ * the caller can read ids and definition lines where they lie.  Owned by the
+ * context until the next upload. */
+int gm_db_records(const gm_ctx *c, const int64_t **rec_off, const int64_t **hdr_off, int *n_rec);
+
+/* Characters [off, off + n) of the uploaded batch (forward strand) as fm_sbuf
+ * holds them: lower case, u -> t (src/dbutil.c:105-111).  Device -> host copy. */
+int gm_db_get_chars(gm_ctx *c, int64_t off, int64_t n, char *out);
+
 /* Number of nucleotides in the uploaded batch. */
 int64_t gm_db_total_nt(const gm_ctx *c);
 
@@ -112,6 +134,16 @@ int gm_scan_finish(gm_ctx *c);
  * gm_hit_hdr_t followed by n_descr gm_hit_el_t (include/gpumotif_plan.h).
  * Owned by the context until the next scan. */
 int gm_hits(const gm_ctx *c, const void **hits, size_t *n, size_t *stride);
+
+/* The searched strand around each candidate of the last scan, in gm_hits()
+ * order: window i is *stride characters, the ones fm_sbuf holds (lower case,
+ * u -> t, src/dbutil.c:105-111; on the complementary strand mk_rcmp's letters,
+ * src/rnamot.c:193-216) at strand offsets [szero_i - lead, szero_i - lead +
+ * *stride); offsets outside the record read as 0.  *stride >= lead + w_winsize
+ * + trail + 1.  This is what print_match and the score program read
+ * (src/find_motif.c:1826-1898, src/score.c:1440-1484,2127,3110-3237), so a caller
+ * that keeps no sequence on the host passes `win_i - (szero_i - lead)` as sbuf. */
+int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, size_t *stride);
 
 int gm_stats(const gm_ctx *c, gm_scan_stats_t *out);
 

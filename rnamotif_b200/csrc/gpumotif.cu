@@ -19,6 +19,7 @@
 
 #include "gpumotif.h"
 #include "gm_machine.cuh"
+#include "gm_fastn.cuh"
 
 using namespace gm;
 
@@ -66,6 +67,19 @@ struct gm_ctx {
 	size_t rec_cap;
 	std::vector<int64_t> rec_off;
 	int64_t total_nt;
+	// FASTA text parsed on the device (gm_db_upload_fastn)
+	uint8_t *d_text;
+	size_t text_cap;
+	int64_t *d_hdr_off;
+	size_t hdr_cap;          // bytes
+	void *d_fsum, *d_fstart; // per-segment summaries / starts
+	size_t fsum_cap, fstart_cap;
+	std::vector<int64_t> hdr_off;
+	const uint8_t *d_seq_chars; // the uploaded characters as they sit on the device (window gather)
+	// windows around the candidates (gm_hit_windows)
+	uint8_t *d_win, *h_win;
+	size_t win_cap, h_win_cap;
+	std::vector<uint8_t> wins;
 	// scan
 	unsigned long long *d_counters; // [0] tile, [1] hits, [2] starts
 	uint32_t *d_hits;
@@ -589,6 +603,13 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	gm_ctx *c = new gm_ctx();
 	memset(&c->stats, 0, sizeof c->stats);
 	c->d_chars = c->d_packed = NULL;
+	c->d_text = NULL;
+	c->d_hdr_off = NULL;
+	c->d_fsum = c->d_fstart = NULL;
+	c->text_cap = c->hdr_cap = c->fsum_cap = c->fstart_cap = 0;
+	c->d_seq_chars = NULL;
+	c->d_win = c->h_win = NULL;
+	c->win_cap = c->h_win_cap = 0;
 	c->d_rec_off = NULL;
 	c->d_counters = NULL;
 	c->d_hits = NULL;
@@ -686,6 +707,12 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 	if (c->copy_stream)
 		cudaStreamDestroy(c->copy_stream);
 	cudaFree(c->d_chars);
+	cudaFree(c->d_text);
+	cudaFree(c->d_hdr_off);
+	cudaFree(c->d_fsum);
+	cudaFree(c->d_fstart);
+	cudaFree(c->d_win);
+	cudaFreeHost(c->h_win);
 	cudaFree(c->d_packed);
 	cudaFree(c->d_rec_off);
 	cudaFree(c->d_counters);
@@ -749,6 +776,7 @@ static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
 			return fail("record %d longer than 2^31", r);
 	}
 	c->rec_off.assign(rec_off, rec_off + n_rec + 1);
+	c->hdr_off.clear();
 	c->total_nt = rec_off[n_rec];
 	size_t cap_bytes = c->rec_cap * sizeof(int64_t);
 	if (ensure((void **)&c->d_rec_off, &cap_bytes, (size_t)(n_rec + 1) * sizeof(int64_t)))
@@ -761,7 +789,7 @@ static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
 
 // Enqueue the upload on copy_stream in chunks: [H2D copy of chunk i,] pack chunk i,
 // record chunk_ev[i].  Returns without waiting.
-static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src)
+static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src, bool mark_start = true)
 {
 	const int64_t n = c->total_nt;
 	const size_t pbytes = (size_t)(((n + 15) / 16) * 8) + 1024; // slack: kernels read whole 16-byte groups past the end
@@ -780,7 +808,9 @@ static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src
 		c->chunk_ev.push_back(e);
 	}
 	c->chunk_end.clear();
-	CU(cudaEventRecord(c->up_ev[0], c->copy_stream));
+	c->d_seq_chars = h_chars != NULL ? c->d_chars : d_src;
+	if (mark_start)
+		CU(cudaEventRecord(c->up_ev[0], c->copy_stream));
 	for (int i = 0; i < n_chunks; i++) {
 		const int64_t o = (int64_t)i * chunk, len = std::min<int64_t>(chunk, n - o);
 		const uint8_t *src = d_src;
@@ -833,6 +863,117 @@ extern "C" int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_
 	if (upload_chunks(c, NULL, (const uint8_t *)d_seq))
 		return -1;
 	c->stats.h2d_bytes = (uint64_t)(n_rec + 1) * 8;
+	return 0;
+}
+
+// FN_fgetseq on the device, src/dbutil.c:42-128 (gm_fastn.cuh): text -> kept
+// characters + record table -> 4-bit codes.
+extern "C" int gm_db_upload_fastn(gm_ctx *c, const char *text, size_t n_bytes)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	if (c->pending)
+		return fail("a scan is in flight");
+	if (n_bytes > 0 && text == NULL)
+		return fail("text is NULL");
+	if (n_bytes > ((size_t)1 << 40))
+		return fail("text too long");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	if (n_bytes > 0 && text[0] != '>')
+		return fail("fastn text does not begin with '>' (src/dbutil.c:56-60)");
+	const int64_t n = (int64_t)n_bytes;
+	const int n_seg = (int)((n + GM_FASTN_SEG - 1) / GM_FASTN_SEG);
+	if (ensure((void **)&c->d_text, &c->text_cap, n_bytes + 64) ||
+	    ensure((void **)&c->d_chars, &c->chars_cap, n_bytes + 64) ||
+	    ensure(&c->d_fsum, &c->fsum_cap, (size_t)(n_seg + 1) * sizeof(FastnSum) + 16) ||
+	    ensure(&c->d_fstart, &c->fstart_cap, (size_t)(n_seg + 1) * sizeof(FastnSegStart)))
+		return -1;
+	unsigned long long *d_tot = reinterpret_cast<unsigned long long *>(
+		static_cast<uint8_t *>(c->d_fsum) + (size_t)(n_seg + 1) * sizeof(FastnSum));
+	CU(cudaEventRecord(c->up_ev[0], c->copy_stream));
+	unsigned long long tot[2] = {0, 0};
+	if (n > 0) {
+		CU(cudaMemcpyAsync(c->d_text, text, n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+		const int blocks = (n_seg * 32 + 255) / 256;
+		gm_fastn_summarize<<<blocks, 256, 0, c->copy_stream>>>(c->d_text, n, static_cast<FastnSum *>(c->d_fsum), n_seg);
+		CU(cudaGetLastError());
+		gm_fastn_scan<<<1, 1024, 0, c->copy_stream>>>(static_cast<const FastnSum *>(c->d_fsum), n_seg,
+			static_cast<FastnSegStart *>(c->d_fstart), d_tot);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, c->copy_stream));
+		CU(cudaStreamSynchronize(c->copy_stream));
+	}
+	if (tot[1] > 0x7ffffff0ull)
+		return fail("too many records in one upload");
+	const int n_rec = (int)tot[1];
+	const size_t tab = (size_t)(n_rec + 1) * sizeof(int64_t);
+	size_t cap_bytes = c->rec_cap * sizeof(int64_t);
+	if (ensure((void **)&c->d_rec_off, &cap_bytes, tab))
+		return -1;
+	c->rec_cap = cap_bytes / sizeof(int64_t);
+	if (ensure((void **)&c->d_hdr_off, &c->hdr_cap, tab))
+		return -1;
+	c->rec_off.resize(n_rec + 1);
+	c->hdr_off.resize(n_rec + 1);
+	if (n > 0) {
+		const int blocks = (n_seg * 32 + 255) / 256;
+		gm_fastn_emit<<<blocks, 256, 0, c->copy_stream>>>(c->d_text, n, static_cast<const FastnSegStart *>(c->d_fstart),
+			n_seg, c->d_chars, c->d_rec_off, c->d_hdr_off);
+		CU(cudaGetLastError());
+	}
+	const int64_t last[2] = {(int64_t)tot[0], n};
+	CU(cudaMemcpyAsync(c->d_rec_off + n_rec, &last[0], sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
+	CU(cudaMemcpyAsync(c->d_hdr_off + n_rec, &last[1], sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
+	CU(cudaMemcpyAsync(c->rec_off.data(), c->d_rec_off, tab, cudaMemcpyDeviceToHost, c->copy_stream));
+	CU(cudaMemcpyAsync(c->hdr_off.data(), c->d_hdr_off, tab, cudaMemcpyDeviceToHost, c->copy_stream));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	c->total_nt = (int64_t)tot[0];
+	if (c->rec_off[0] != 0)
+		return fail("fastn text has sequence before its first header");
+	for (int r = 0; r < n_rec; r++)
+		if (c->rec_off[r + 1] - c->rec_off[r] > 0x7ffffff0ll)
+			return fail("record %d longer than 2^31", r);
+	if (upload_chunks(c, NULL, c->d_chars, false))
+		return -1;
+	c->stats.h2d_bytes = (uint64_t)n_bytes;
+	return 0;
+}
+
+extern "C" int gm_db_records(const gm_ctx *c, const int64_t **rec_off, const int64_t **hdr_off, int *n_rec)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	if (c->rec_off.empty())
+		return fail("no database uploaded");
+	if (rec_off)
+		*rec_off = c->rec_off.data();
+	if (hdr_off)
+		*hdr_off = c->hdr_off.size() == c->rec_off.size() ? c->hdr_off.data() : NULL;
+	if (n_rec)
+		*n_rec = (int)c->rec_off.size() - 1;
+	return 0;
+}
+
+// Characters [off, off + n) of the uploaded batch (forward strand), as fm_sbuf
+// holds them: lower case, u -> t (src/dbutil.c:105-111).
+extern "C" int gm_db_get_chars(gm_ctx *c, int64_t off, int64_t n, char *out)
+{
+	if (c == NULL || out == NULL || off < 0 || n < 0)
+		return fail("bad argument");
+	if (c->d_seq_chars == NULL)
+		return fail("no database uploaded");
+	if (off + n > c->total_nt)
+		return fail("range [%lld, %lld) outside the %lld uploaded nucleotides", (long long)off, (long long)(off + n),
+			    (long long)c->total_nt);
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	if (n > 0)
+		CU(cudaMemcpy(out, c->d_seq_chars + off, (size_t)n, cudaMemcpyDeviceToHost));
+	for (int64_t i = 0; i < n; i++) {
+		unsigned ch = (unsigned char)out[i] | 0x20;
+		out[i] = ch == 'u' ? 't' : (char)ch;
+	}
 	return 0;
 }
 
@@ -1074,6 +1215,53 @@ extern "C" int gm_hits(const gm_ctx *c, const void **hits, size_t *n, size_t *st
 		*n = c->n_hits;
 	if (stride)
 		*stride = (size_t)c->stride_words * 4;
+	return 0;
+}
+
+// The searched strand around every candidate of the last scan, for callers that
+// never had the sequence on the host (gm_db_upload_fastn): what fm_sbuf holds
+// at strand offsets [szero - lead, szero + w_winsize + trail), in gm_hits() order.
+extern "C" int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, size_t *stride)
+{
+	if (c == NULL || lead < 0 || trail < 0 || lead > 30000 || trail > 30000)
+		return fail("bad argument");
+	if (c->pending)
+		return fail("a scan is in flight");
+	if (c->d_seq_chars == NULL)
+		return fail("no database uploaded");
+	CU(cudaSetDevice(c->device));
+	const int wlen = (lead + c->par.w_winsize + trail + 1 + 7) & ~7;
+	const size_t n = c->n_hits;
+	const size_t bytes = n * (size_t)wlen;
+	if (ensure((void **)&c->d_win, &c->win_cap, bytes + 16))
+		return -1;
+	if (bytes > c->h_win_cap) {
+		cudaFreeHost(c->h_win);
+		c->h_win = NULL;
+		c->h_win_cap = 0;
+		const size_t want = bytes + bytes / 4 + 4096;
+		CU(cudaMallocHost(&c->h_win, want));
+		c->h_win_cap = want;
+	}
+	if (n > 0) {
+		const int blocks = (int)std::min<size_t>(n, (size_t)c->n_sm * 32);
+		gm_window_kernel<<<blocks, 128, 0, c->stream>>>(c->d_seq_chars, c->d_rec_off, c->d_hits, n, c->stride_words,
+			lead, wlen, c->d_win);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(c->h_win, c->d_win, bytes, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+	}
+	// the device wrote them in hit-buffer order; gm_scan_finish left the sorted
+	// order in the keys
+	if (c->wins.size() < bytes)
+		c->wins.resize(bytes + bytes / 4);
+	for (size_t i = 0; i < n; i++)
+		memcpy(&c->wins[i * wlen], c->h_win + (size_t)(uint32_t)c->keys[2 * i + 1] * wlen, wlen);
+	c->stats.d2h_bytes += bytes;
+	if (win)
+		*win = reinterpret_cast<const char *>(c->wins.data());
+	if (stride)
+		*stride = (size_t)wlen;
 	return 0;
 }
 

@@ -33,7 +33,8 @@ class GpuMotifError(RuntimeError):
 _lib = None
 
 EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_ctx_create", "gm_ctx_destroy",
-           "gm_plan_check", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_total_nt",
+           "gm_plan_check", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
+           "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
            "gm_set_hit_capacity", "gm_set_tile", "gm_stream"]
 
@@ -53,6 +54,10 @@ def lib():
         L.gm_plan_check.argtypes = [C.c_char_p]
         L.gm_db_upload_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gm_db_set_device_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.gm_db_upload_fastn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.gm_db_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.gm_hit_windows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.gm_db_get_chars.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.gm_db_total_nt.argtypes = [C.c_void_p]
         L.gm_db_total_nt.restype = C.c_int64
         L.gm_scan.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int]
@@ -147,6 +152,48 @@ class MotifSearch:
         rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
         self._ck(lib().gm_db_set_device_chars(self._ctx, dev_ptr, rec_off.ctypes.data, len(rec_off) - 1),
                  "gm_db_set_device_chars")
+
+    def upload_fastn(self, text):
+        """gm_db_upload_fastn: `text` = FASTA as it sits in the file (bytes or a uint8
+        array); the reader of src/dbutil.c:42-128 runs on the device."""
+        if isinstance(text, (bytes, bytearray, memoryview)):
+            text = np.frombuffer(text, dtype=np.uint8)
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        self._keep = text
+        self._ck(lib().gm_db_upload_fastn(self._ctx, text.ctypes.data, text.size), "gm_db_upload_fastn")
+
+    def upload_fastn_ptr(self, host_ptr: int, n_bytes: int):
+        self._ck(lib().gm_db_upload_fastn(self._ctx, host_ptr, n_bytes), "gm_db_upload_fastn")
+
+    def records(self):
+        """(rec_off, hdr_off) of the uploaded batch; hdr_off is None unless it came
+        through upload_fastn."""
+        ro, ho, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        self._ck(lib().gm_db_records(self._ctx, C.byref(ro), C.byref(ho), C.byref(n)), "gm_db_records")
+        m = n.value + 1
+        rec = np.frombuffer((C.c_int64 * m).from_address(ro.value), dtype=np.int64).copy()
+        hdr = np.frombuffer((C.c_int64 * m).from_address(ho.value), dtype=np.int64).copy() if ho.value else None
+        return rec, hdr
+
+    def get_chars(self, off: int = 0, n: int | None = None):
+        """gm_db_get_chars: the uploaded characters (lower case, u -> t) as a uint8 array."""
+        if n is None:
+            n = self.total_nt - off
+        out = np.empty(max(n, 0), dtype=np.uint8)
+        self._ck(lib().gm_db_get_chars(self._ctx, off, n, out.ctypes.data), "gm_db_get_chars")
+        return out
+
+    def hit_windows(self, lead: int = 0, trail: int = 0):
+        """gm_hit_windows: uint8 array [n_hits, stride]; row i = the searched strand from
+        offset szero_i - lead on, as fm_sbuf would hold it."""
+        p, st = C.c_void_p(), C.c_size_t()
+        self._ck(lib().gm_hit_windows(self._ctx, lead, trail, C.byref(p), C.byref(st)), "gm_hit_windows")
+        n = C.c_size_t()
+        self._ck(lib().gm_hits(self._ctx, None, C.byref(n), None), "gm_hits")
+        if n.value == 0:
+            return np.zeros((0, st.value), dtype=np.uint8)
+        buf = (C.c_uint8 * (n.value * st.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(n.value, st.value).copy()
 
     @property
     def total_nt(self) -> int:
