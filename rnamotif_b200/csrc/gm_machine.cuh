@@ -124,7 +124,7 @@ struct PairBits {
 // starts at window position z can have its first `req` pairs formed with at
 // most `budget` mispairs -- a superset of the span ends match_wchlx accepts.
 // bit j of the result <-> s3 = lo + j.
-__device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
+__device__ __noinline__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
 	int dupi, int flt, int z, int lo, int n)
 {
 	const uint64_t ones = n >= 64 ? ~0ull : ((1ull << n) - 1);
@@ -164,6 +164,138 @@ __device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, i
 	return (budget == 0 ? a0 : budget == 1 ? a1 : a2) & ones;
 }
 
+// The level-0 sieve: the span-end test of wc_mask for 32 consecutive helix
+// starts at once, one lane per 32-bit word of starts, word operations only.
+// With M_d = { p : nucleotides p and p + d can pair } (built from the pair
+// bitsets P[x] and the base bitsets I[x] = { p : base(p) = x }) the helix that
+// starts at z and spans to z + D has its pair k at (z + k, z + D - k), i.e. bit
+// z + k of M_{D-2k}.  Going through d upwards, M_d is computed once and ANDed
+// (shifted by k) into the running products of the eight span offsets D = d + 2k
+// it belongs to; the product of D = d is complete at that step.  Bit t of the
+// result: some span offset in [Dlo, Dhi] lets the first `req` pairs of a helix
+// starting at tile position 32 w + t form within the budget (0 or 1) -- what
+// wc_mask(...) != 0 says for that start when the window is not clipped, and a
+// superset of it when it is.
+// `fin(d, f)` sees every completed span offset d >= Dlo with its word f and
+// returns what of it counts (the identity, a look-ahead filter, ...).
+template <typename Fin>
+__device__ __forceinline__ uint32_t sieve_word(const PairBits &pb, int strand, int dupi, int flt, int w, int Dlo, int Dhi, Fin fin)
+{
+	const int req = flt & 0xff, budget = (flt >> 8) & 0xff, first_must = (flt >> 16) & 1;
+	const int nwb = pb.nwb;
+	const uint32_t *P = pb.base + ((size_t)(strand * pb.n_dups + dupi) * 4) * nwb;
+	const uint32_t *I = pb.base + ((size_t)(strand * pb.n_dups) * 4) * nwb; // table 0: base bitsets
+	uint32_t Bl[4], Bh[4];
+#pragma unroll
+	for (int x = 0; x < 4; x++) {
+		Bl[x] = I[x * nwb + w];
+		Bh[x] = I[x * nwb + w + 1];
+	}
+	uint32_t res = 0;
+	const int Dmin = Dlo - 2 * (req - 1);
+	for (int par = 0; par < 2; par++) {
+		// a0[k] / a1[k]: products (no mispair / at most one) of the span offset that
+		// is k steps from completion; the loop is kept rolled (rotating the
+		// registers) so that it stays inside the L0 instruction cache
+		uint32_t a0[8], a1[8];
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+			a0[u] = a1[u] = ~0u;
+		for (int d = Dmin + par; d <= Dhi; d += 2) {
+			const int ww = min(w + (d >> 5), nwb - 3), sh = d & 31;
+			uint32_t Ml = 0, Mh = 0;
+#pragma unroll
+			for (int x = 0; x < 4; x++) {
+				const uint32_t c0 = P[x * nwb + ww], c1 = P[x * nwb + ww + 1], c2 = P[x * nwb + ww + 2];
+				Ml |= Bl[x] & __funnelshift_r(c0, c1, sh);
+				Mh |= Bh[x] & __funnelshift_r(c1, c2, sh);
+			}
+#pragma unroll
+			for (int k = 7; k >= 1; k--) {
+				if (k < req) {
+					const uint32_t t = __funnelshift_r(Ml, Mh, k);
+					a1[k] = (a1[k] & t) | a0[k];
+					a0[k] &= t;
+				}
+			}
+			// the outermost pair closes span offset D = d (see wc_mask for the rules)
+			uint32_t f;
+			if (first_must)
+				f = (budget ? a1[0] : a0[0]) & Ml;
+			else if (budget == 0)
+				f = a0[0];
+			else
+				f = (a1[0] & Ml) | a0[0];
+			if (d >= Dlo)
+				res |= fin(d, f);
+#pragma unroll
+			for (int u = 0; u < 7; u++) {
+				a0[u] = a0[u + 1];
+				a1[u] = a1[u + 1];
+			}
+			a0[7] = a1[7] = ~0u;
+		}
+	}
+	return res;
+}
+
+// 32 bits of a bitset from bit q on (q >= 0)
+__device__ __forceinline__ uint32_t bits32(const uint32_t *set, int q)
+{
+	return __funnelshift_r(set[q >> 5], set[(q >> 5) + 1], q & 31);
+}
+
+// The mirror image of wc_mask: the helix's 3' END e is known and its 5' start is
+// not.  5' starts zt in [zlo, zlo+n) (n <= 64) at which the first `req` pairs
+// (zt+k, e-k) can form within the budget; bit j <-> zt = zlo + j.  `dupi_t`
+// indexes the bitsets of the TRANSPOSED duplex table (bit p of set y = the
+// nucleotide at p, as 5' base, pairs with 3' base y).
+__device__ __noinline__ uint64_t wc_mask_rev(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
+	int dupi_t, int flt, int e, int zlo, int n)
+{
+	const uint64_t ones = n >= 64 ? ~0ull : ((1ull << n) - 1);
+	const int req = flt & 0xff, budget = (flt >> 8) & 0xff, first_must = (flt >> 16) & 1;
+	if (dupi_t < 0 || req == 0)
+		return ones;
+	const uint32_t *sets = pb.base + ((size_t)(strand * pb.n_dups + dupi_t) * 4) * pb.nwb;
+	uint64_t a0 = ones, a1 = ones, a2 = ones;
+	for (int k = 0; k < req; k++) {
+		const int y = bcode_of(sq[e - k]);
+		uint64_t m = 0;
+		if (y < 4)
+			m = bits64(sets + y * pb.nwb, sqbase + zlo + k);
+		if (k == 0 && first_must) {
+			a0 = a1 = a2 = m;
+		} else if (k == 0 && budget == 0) {
+			// see wc_mask: an outermost mispair is tolerated without a budget
+		} else {
+			a2 = (a2 & m) | a1;
+			a1 = (a1 & m) | a0;
+			a0 &= m;
+		}
+	}
+	return (budget == 0 ? a0 : budget == 1 ? a1 : a2) & ones;
+}
+
+// Tail look-ahead (DevSearch::lk_t): with helix S chosen as (s5, s3, hl), can the
+// last helix group T of its interior chain form at all?  T ends at
+// e = s3 - hl - lk_off and begins somewhere in [e - maxglen + 1, e - minglen + 1],
+// not before the interior does.  Pure pruning: a false answer means no
+// assignment of the interior reaches the hit sink.
+__device__ __forceinline__ bool tail_feasible(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
+	const DevSearch &S, const DevSearch &T, int s5, int s3, int hl)
+{
+	const int e = s3 - hl - S.lk_off;
+	int zhi = e - T.minglen + 1;
+	const int zlo = max(e - T.maxglen + 1, s5 + hl);
+	for (; zhi >= zlo; zhi -= 64) {
+		const int l0 = max(zlo, zhi - 63);
+		if (wc_mask_rev(pb, sq, strand, sqbase, T.dupi_t, T.flt, e, l0, zhi - l0 + 1) != 0)
+			return true;
+	}
+	return false;
+}
+
 // MODE 0: fused -- prefilter and machine in one kernel (works for every plan).
 // MODE 1: prefilter only -- survivors are appended to a global worklist that
 //         gm_dfs_kernel consumes (the split path).
@@ -179,18 +311,21 @@ __device__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, i
 // helices only (most descriptors): the pseudoknot / parallel helix / triplex /
 // quadruplex code is left out, which keeps the hot loop inside the
 // instruction cache.
-// LIT = true adds the literal prefilter (plans with a gm_plan_t::literal); a
-// template parameter so that plans without one run exactly the code they had
-// before it existed.
-template <int MODE, bool FULL, bool LIT>
+// PF selects the level-0 prefilter: 0 = per-start candidate mask, 1 = the same
+// plus the literal prefilter (plans with a gm_plan_t::literal), 2 = the
+// word-parallel sieve (sieve_word).  A template parameter so that each plan
+// runs only the code it needs (the kernel is instruction-cache bound).
+template <int MODE, bool FULL, int PF>
 __global__ void gm_search_kernel(const ScanArgs A)
 {
+	constexpr bool LIT = PF == 1;   // literal prefilter
+	constexpr bool SIEVE = PF == 2; // word-parallel level-0 sieve instead of the per-start prefilter
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, nt = blockDim.x;
 	const int lane = tid & 31, warp = tid >> 5;
 	const int NS = c_par.n_searches, ND = c_par.n_descr;
 	const int W = c_par.w_winsize, H = c_par.halo, TILE = c_par.tile;
-	const int Lbytes = (TILE + 2 * H + 15) & ~15;          // nucleotides staged per tile
+	const int Lbytes = (TILE + 2 * H + 31) & ~31;          // nucleotides staged per tile (whole bitset words)
 	const int stage_bytes = ((Lbytes >> 1) + 32 + 15) & ~15; // packed staging (+ alignment slack)
 	const int nwb = ((Lbytes + 31) >> 5) + 4;
 	const int n_dups = c_par.n_dups;
@@ -202,7 +337,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	const size_t pb_bytes = (((size_t)2 * n_dups * 4 * nwb * 4) + 15) & ~(size_t)15;
 	const size_t lit_bytes = LIT ? (((size_t)2 * nwb * 4) + 15) & ~(size_t)15 : 0;
 	const size_t buf_bytes = 2 * (size_t)Lbytes + pb_bytes + (GM_REC_CACHE + 2) * 8 + lit_bytes;
-	const size_t warp_bytes = 16 + (size_t)stage_bytes + NBUF * buf_bytes + GM_QCAP * 2;
+	const size_t warp_bytes = 16 + (size_t)stage_bytes + NBUF * buf_bytes + GM_QCAP * 2 + (SIEVE ? ((6 * (size_t)nwb * 4 + 15) & ~(size_t)15) : 0);
 	uint8_t *p = smem_raw;
 	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
 	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
@@ -214,6 +349,15 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	uint8_t *sm_stage = wp;                                    wp += stage_bytes;
 	uint8_t *bufs = wp;                                        wp += NBUF * buf_bytes;
 	uint16_t *myq = reinterpret_cast<uint16_t *>(wp);
+	// look-ahead bitsets of the sieve (DevParams::pf_deep), per strand: sv_E = ends
+	// at which the last helix of the first helix's interior can form, sv_K =
+	// starts at which its first helix can
+	uint32_t *sv_E = reinterpret_cast<uint32_t *>(myq + GM_QCAP);
+	uint32_t *sv_K = sv_E + 2 * nwb;
+	uint32_t *sv_K2 = sv_K + 2 * nwb; // starts at which the helix FOLLOWING that first helix can form (pf_deep == 2)
+	const bool deep = SIEVE && c_par.pf_deep != 0;
+	const int sv_nws = ((TILE - 1) >> 5) + 2;               // sieve words per strand
+	const int sv_npass = (A.strands * sv_nws + 31) >> 5;
 
 	// stage the hot plan tables
 	for (int i = tid; i < NS * (int)(sizeof(DevSearch) / 4); i += nt)
@@ -251,6 +395,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 
 	uint32_t parity = 0;
 	unsigned long long my_starts = 0;
+	unsigned my_entries = 0; // starts handed to the machine (debug statistics)
 
 	// current tile (warp-uniform)
 	int cur = NBUF - 1;          // buffer of the current tile (first load flips it to 0)
@@ -316,8 +461,13 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		}
 		mbar_wait(&sm->bar, parity);
 		parity ^= 1;
-		// expand packed nibbles to one byte per nucleotide, both strands
-		for (int i = lane; i < Lbytes; i += 32) {
+		// expand packed nibbles to one byte per nucleotide, both strands, and build
+		// the forward base bitsets (set 0 = the identity table: bit p of set x says
+		// base(p) == x) with four ballots per 32 nucleotides
+		uint32_t *pbw = const_cast<uint32_t *>(pb.base);
+		const int nw = Lbytes >> 5;
+		for (int w = 0; w < nw; w++) {
+			const int i = (w << 5) + lane;
 			const int64_t g = lo + i;
 			uint8_t v = (uint8_t)(4 << 4);
 			if (g >= 0 && g < A.total_nt) {
@@ -326,23 +476,42 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			}
 			sm_fwd[i] = v;
 			sm_rc[Lbytes - 1 - i] = complement_byte(v);
+			const int bc = bcode_of(v);
+			const unsigned u0 = __ballot_sync(0xffffffffu, bc == 0);
+			const unsigned u1 = __ballot_sync(0xffffffffu, bc == 1);
+			const unsigned u2 = __ballot_sync(0xffffffffu, bc == 2);
+			const unsigned u3 = __ballot_sync(0xffffffffu, bc == 3);
+			if (lane < 4)
+				pbw[(size_t)lane * nwb + w] = lane == 0 ? u0 : lane == 1 ? u1 : lane == 2 ? u2 : u3;
 		}
+		if (lane < 4 * (nwb - nw))
+			pbw[(size_t)(lane / (nwb - nw)) * nwb + nw + lane % (nwb - nw)] = 0; // padding words
 		__syncwarp();
-		// pair bitsets: one ballot per (strand, table, base) and 32 positions
-		uint32_t *pbw = const_cast<uint32_t *>(pb.base);
-		for (int w = 0; w < nwb; w++) {
-			const int i = w * 32 + lane;
-			const int vf = i < Lbytes ? bcode_of(sm_fwd[i]) : 4;
-			const int vr = i < Lbytes ? bcode_of(sm_rc[i]) : 4;
-			for (int dd = 0; dd < n_dups; dd++) {
-				const unsigned dup = c_par.dups[dd];
-				for (int x = 0; x < 4; x++) {
-					const unsigned bf = __ballot_sync(0xffffffffu, (dup >> (x * 5 + vf)) & 1u);
-					const unsigned br = __ballot_sync(0xffffffffu, (dup >> (x * 5 + vr)) & 1u);
-					if (lane == 0) {
-						pbw[((size_t)(0 * n_dups + dd) * 4 + x) * nwb + w] = bf;
-						pbw[((size_t)(1 * n_dups + dd) * 4 + x) * nwb + w] = br;
-					}
+		// reverse-complement base bitsets: position i of that strand holds the
+		// complement of forward position Lbytes-1-i, so word w of set x is the
+		// bit-reversed word nw-1-w of forward set 3-x
+		for (int x = 0; x < 4; x++)
+			for (int w = lane; w < nwb; w += 32)
+				pbw[((size_t)(n_dups * 4) + x) * nwb + w] = w < nw ? __brev(pbw[(size_t)(3 - x) * nwb + nw - 1 - w]) : 0u;
+		__syncwarp();
+		// pair bitsets of every other table: set x = union of the base bitsets of
+		// the bases x pairs with, one word per lane
+		for (int sd = 0; sd < 2 * n_dups; sd++) {
+			const int st = sd >= n_dups, dd = st ? sd - n_dups : sd;
+			if (dd == 0)
+				continue;
+			const unsigned dup = c_par.dups[dd];
+			const uint32_t *bs_ = pbw + (size_t)(st * n_dups) * 4 * nwb;
+			uint32_t *out = pbw + (size_t)(st * n_dups + dd) * 4 * nwb;
+			for (int x = 0; x < 4; x++) {
+				const unsigned row = dup >> (x * 5);
+				for (int w = lane; w < nwb; w += 32) {
+					uint32_t acc = 0;
+#pragma unroll
+					for (int y = 0; y < 4; y++)
+						if ((row >> y) & 1u)
+							acc |= bs_[(size_t)y * nwb + w];
+					out[(size_t)x * nwb + w] = acc;
 				}
 			}
 		}
@@ -499,42 +668,205 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		return pass;
 	};
 
+	// what is left of the prefilter for a start the sieve let through: is it a
+	// start of this scan at all, and can an anchored seq= of search 0 match
+	auto accept = [&](int q) -> bool {
+		int comp, idx, slen, szero;
+		uint32_t rec;
+		if (!locate(q, comp, idx, rec, slen, szero))
+			return false;
+		const DevSearch &S0 = sm_ds[0];
+		if (S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
+			const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
+			const int dl = min(W, slen - szero) - 1;
+			return rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
+		}
+		return true;
+	};
+
+	// ---- the sieve (PF == 2), shared by the fused and the prefilter-only kernel ----
+	// look-ahead bitsets for the current tile, one word per lane: over the range
+	// of positions the main pass can ask about
+	auto sieve_aux = [&]() {
+		const DevSearch &SP = sm_ds[c_par.pf_search];
+		const int nw = Lbytes >> 5;
+		for (int i = lane; i < 2 * nwb; i += 32) {
+			sv_E[i] = 0;
+			sv_K[i] = 0;
+			sv_K2[i] = 0;
+		}
+		__syncwarp();
+		const int nv = (int)(gB - gA);
+		for (int st = 0; st < A.strands; st++) {
+			const int zlo = (st ? Lbytes - H - nv : H) + c_par.pf_z, zhi = zlo + nv - 1; // helix starts of this tile
+			if (SP.lk_t >= 0) {
+				// ends asked about: zb + d - hl - lk_off; the helices that end there start
+				// up to maxglen - 1 earlier
+				const DevSearch &T = sm_ds[SP.lk_t];
+				const int lo_ = max(zlo + SP.minglen - 1 - SP.maxlen - SP.lk_off - (T.maxglen - 1), 0);
+				const int hi_ = min(zhi + SP.maxglen - 1 - SP.minlen - SP.lk_off - (T.minglen - 1), Lbytes - 1);
+				uint32_t *E = sv_E + st * nwb;
+				for (int w = (lo_ >> 5) + lane; w <= (hi_ >> 5) && w < nw; w += 32)
+					sieve_word(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
+						[&](int d, uint32_t f) -> uint32_t {
+							// the helix that starts at bit t ends at t + d
+							const int q = (w << 5) + d, sh = q & 31;
+							if (f != 0) {
+								if ((q >> 5) < nwb)
+									atomicOr(E + (q >> 5), f << sh);
+								if (sh && (q >> 5) + 1 < nwb)
+									atomicOr(E + (q >> 5) + 1, f >> (32 - sh));
+							}
+							return 0u;
+						});
+			}
+			if (SP.kid_t >= 0) {
+				const DevSearch &T = sm_ds[SP.kid_t];
+				const int lo_ = zlo + SP.minlen + SP.kid_off;
+				const int hi_ = min(zhi + SP.maxlen + SP.kid_off + 31, Lbytes - 1);
+				const bool has_k2 = c_par.pf_deep == 2;
+				const uint32_t *K2 = sv_K2 + st * nwb;
+				if (has_k2) {
+					// the helix after the first interior helix starts sib_off + 1 behind its
+					// group: sieve its starts first, over everything the next loop asks about
+					const DevSearch &T2 = sm_ds[T.sib_t];
+					const int lo2 = (lo_ & ~31) + T.minglen + T.sib_off;
+					const int hi2 = min((hi_ | 31) + T.maxglen + T.sib_off + 31, Lbytes - 1);
+					for (int w = (lo2 >> 5) + lane; w <= (hi2 >> 5) && w < nw; w += 32)
+						sv_K2[st * nwb + w] = sieve_word(pb, st, T2.dupi, T2.flt, w, T2.minglen - 1, T2.maxglen - 1,
+							[](int, uint32_t f) -> uint32_t { return f; });
+					__syncwarp();
+				}
+				const int k2off = T.sib_off + 1;
+				for (int w = (lo_ >> 5) + lane; w <= (hi_ >> 5) && w < nw; w += 32)
+					sv_K[st * nwb + w] = sieve_word(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
+						[&](int d, uint32_t f) -> uint32_t {
+							// span offset d: the group ends at start + d, its sibling begins k2off later
+							return has_k2 ? f & bits32(K2, min((w << 5) + d + k2off, Lbytes)) : f;
+						});
+			}
+		}
+		__syncwarp();
+	};
+	// the lane's word of pass `pass` over the tile's helix starts (strand-major)
+	auto sieve_pass = [&](int pass, int &strand_, int &w_) -> uint32_t {
+		const DevSearch &SP = sm_ds[c_par.pf_search];
+		const int pz = c_par.pf_z;
+		const int nv = (int)(gB - gA); // starts of this tile
+		const int it = pass * 32 + lane;
+		uint32_t word = 0;
+		strand_ = it / sv_nws;
+		w_ = 0;
+		if (strand_ < A.strands) {
+			const int zlo = (strand_ ? Lbytes - H - nv : H) + pz, zhi = zlo + nv - 1;
+			w_ = (zlo >> 5) + it % sv_nws;
+			if (w_ <= (zhi >> 5)) {
+				// a span offset d counts only if for some helix length hl the first
+				// interior helix can start right after the 5' strand and the last one
+				// can end right before the 3' strand (pf_deep; otherwise kh[0] = all ones)
+				const int nhl = deep ? SP.maxlen - SP.minlen + 1 : 1;
+				const uint32_t *E = sv_E + strand_ * nwb, *K = sv_K + strand_ * nwb;
+				uint32_t kh[4];
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					kh[j] = j < nhl ? (deep && SP.kid_t >= 0 ? bits32(K, (w_ << 5) + SP.minlen + j + SP.kid_off) : ~0u) : 0u;
+				// ends asked about at span offset d: e0 + d + m, m = nhl-1-j for length minlen + j
+				const int e0 = (w_ << 5) - SP.minlen - SP.lk_off - (nhl - 1);
+				const bool has_lk = deep && SP.lk_t >= 0;
+				word = sieve_word(pb, strand_, SP.dupi, SP.flt, w_, SP.minglen - 1, SP.maxglen - 1,
+					[&](int d, uint32_t f) -> uint32_t {
+						if (!has_lk)
+							return f & (kh[0] | kh[1] | kh[2] | kh[3]);
+						const int q = max(e0 + d, 0);
+						const uint32_t x0 = E[q >> 5], x1 = E[(q >> 5) + 1], x2 = E[(q >> 5) + 2];
+						const uint32_t lo_ = __funnelshift_r(x0, x1, q & 31), hi_ = __funnelshift_r(x1, x2, q & 31);
+						uint32_t la = 0;
+#pragma unroll
+						for (int j = 0; j < 4; j++)
+							if (j < nhl)
+								la |= kh[j] & __funnelshift_r(lo_, hi_, nhl - 1 - j);
+						return f & la;
+					});
+				// keep the bits of this tile's own starts
+				const int b0 = w_ << 5;
+				if (zlo > b0)
+					word &= ~0u << (zlo - b0);
+				if (zhi < b0 + 31)
+					word &= ~0u >> (b0 + 31 - zhi);
+			}
+		}
+		return word;
+	};
+	// take the lowest survivor out of a sieve word: its start item
+	auto sieve_pop = [&](uint32_t &word, int strand_, int w_) -> int {
+		const int b = (w_ << 5) + __ffs(word) - 1 - c_par.pf_z; // start, in strand buffer coordinates
+		word &= word - 1;
+		return strand_ ? TILE + (Lbytes - 1 - b - H) : b - H;
+	};
+
 	if (MODE == 1) {
 		// prefilter only: append the survivors to the global worklist
+		auto wl_append = [&](bool pass, int q, uint64_t v0, int have_v0) {
+			const unsigned pm = __ballot_sync(0xffffffffu, pass);
+			if (pm == 0)
+				return;
+			unsigned long long base = 0;
+			const int leader = __ffs(pm) - 1;
+			if (lane == leader) {
+				base = atomicAdd(A.wl_count, (unsigned long long)__popc(pm));
+				// statistics for the host: entries over all segments (it sizes the
+				// segments from the survivor rate) and whether any did not fit
+				atomicAdd(A.wl_count + 3, (unsigned long long)__popc(pm));
+				if (base + __popc(pm) > A.wl_cap)
+					atomicOr(A.wl_count + 4, 1ull);
+			}
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (pass) {
+				const unsigned long long slot = base + __popc(pm & ((1u << lane) - 1));
+				if (slot < A.wl_cap) {
+					int comp, idx, slen, szero;
+					uint32_t rec;
+					locate(q, comp, idx, rec, slen, szero);
+					const int64_t g = lo + idx;
+					uint4 *e = reinterpret_cast<uint4 *>(A.wl + slot * GM_WL_WORDS);
+					e[0] = make_uint4((uint32_t)g, (uint32_t)(g >> 32) | ((uint32_t)comp << 31) |
+						((uint32_t)have_v0 << 30), rec, (uint32_t)slen);
+					e[1] = make_uint4((uint32_t)szero, (uint32_t)v0, (uint32_t)(v0 >> 32), 0u);
+				}
+			}
+		};
 		for (;;) {
 			const int64_t t = next_tile();
 			if (t < 0)
 				break;
 			load_tile(0, t);
-			for (;;) {
-				const int chunk = work_next;
-				work_next += 32;
-				if (chunk >= n_work)
-					break;
-				const int q = chunk + lane;
-				uint64_t v0;
-				int have_v0;
-				const bool pass = prefilter(q, v0, have_v0);
-				const unsigned pm = __ballot_sync(0xffffffffu, pass);
-				if (pm == 0)
-					continue;
-				unsigned long long base = 0;
-				const int leader = __ffs(pm) - 1;
-				if (lane == leader)
-					base = atomicAdd(A.wl_count, (unsigned long long)__popc(pm));
-				base = __shfl_sync(0xffffffffu, base, leader);
-				if (pass) {
-					const unsigned long long slot = base + __popc(pm & ((1u << lane) - 1));
-					if (slot < A.wl_cap) {
-						int comp, idx, slen, szero;
-						uint32_t rec;
-						locate(q, comp, idx, rec, slen, szero);
-						const int64_t g = lo + idx;
-						uint4 *e = reinterpret_cast<uint4 *>(A.wl + slot * GM_WL_WORDS);
-						e[0] = make_uint4((uint32_t)g, (uint32_t)(g >> 32) | ((uint32_t)comp << 31) |
-							((uint32_t)have_v0 << 30), rec, (uint32_t)slen);
-						e[1] = make_uint4((uint32_t)szero, (uint32_t)v0, (uint32_t)(v0 >> 32), 0u);
+			if (SIEVE) {
+				if (deep)
+					sieve_aux();
+				for (int pass_ = 0; pass_ < sv_npass; pass_++) {
+					int st_, w_;
+					uint32_t word = sieve_pass(pass_, st_, w_);
+					while (__ballot_sync(0xffffffffu, word != 0)) {
+						int q = 0;
+						bool pass = false;
+						if (word != 0) {
+							q = sieve_pop(word, st_, w_);
+							pass = accept(q);
+						}
+						wl_append(pass, q, 0, 0);
 					}
+				}
+			} else {
+				for (;;) {
+					const int chunk = work_next;
+					work_next += 32;
+					if (chunk >= n_work)
+						break;
+					const int q = chunk + lane;
+					uint64_t v0;
+					int have_v0;
+					const bool pass = prefilter(q, v0, have_v0);
+					wl_append(pass, q, v0, have_v0);
 				}
 			}
 			__syncwarp();
@@ -542,6 +874,10 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	} else {
 		int s = 0, ph = PH_IDLE;
 		int qhead = 0, qtail = 0; // warp-uniform
+		// level-0 sieve (DevParams::sieve): each lane holds one word of survivors
+		constexpr bool sieve = SIEVE;
+		int sv_pass = 0, sv_strand = 0, sv_w = 0;
+		uint32_t sw = 0;
 
 		// ---- the machine ------------------------------------------------
 		for (;;) {
@@ -551,7 +887,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				// top the queue up: prefilter chunks of 32 start items; when the
 				// tile runs dry move on to the next one in the other buffer
 				while (qtail - qhead < want) {
-					if (!have_tile || work_next >= n_work) {
+					const unsigned sv_left = sieve ? __ballot_sync(0xffffffffu, sw != 0) : 0u;
+					if (!have_tile || (sieve ? (sv_left == 0 && sv_pass >= sv_npass) : work_next >= n_work)) {
 						if (no_more_tiles)
 							break;
 						if (qtail != qhead)
@@ -566,6 +903,30 @@ __global__ void gm_search_kernel(const ScanArgs A)
 							break;
 						}
 						load_tile(nb, t);
+						sv_pass = 0;
+						sw = 0;
+						if (deep)
+							sieve_aux();
+						continue;
+					}
+					if (sieve) {
+						if (sv_left == 0) {
+							sw = sieve_pass(sv_pass, sv_strand, sv_w);
+							sv_pass++;
+							continue;
+						}
+						// every lane with a survivor left hands one over
+						int q = 0;
+						bool pass = false;
+						if (sw != 0) {
+							q = sieve_pop(sw, sv_strand, sv_w);
+							pass = accept(q);
+						}
+						const unsigned pm = __ballot_sync(0xffffffffu, pass);
+						if (pass)
+							myq[(qtail + __popc(pm & ((1u << lane) - 1))) & (GM_QCAP - 1)] = (uint16_t)q;
+						qtail += __popc(pm);
+						__syncwarp();
 						continue;
 					}
 					const int chunk = work_next;
@@ -602,6 +963,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					L_ZD(L, 0) = pk16(0, min(W, slen - szero) - 1);
 					s = 0;
 					ph = PH_ENTER;
+					my_entries++;
 				}
 				qhead += min(avail, want);
 				__syncwarp();
@@ -610,9 +972,11 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			}
 
 #define GM_MASK(S, z, clo, n) wc_mask(mypb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n))
+#define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, strand, sqbase, (S), (T), (s5), (s3), (hl))
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
+#undef GM_TAIL
 #undef GM_MASK
 		}
 	}
@@ -622,6 +986,9 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		my_starts += __shfl_down_sync(0xffffffffu, my_starts, o);
 	if (lane == 0 && my_starts)
 		atomicAdd(A.start_count, my_starts);
+	my_entries = __reduce_add_sync(0xffffffffu, my_entries);
+	if (lane == 0 && my_entries)
+		atomicAdd(A.start_count + 3, (unsigned long long)my_entries);
 }
 
 // First-pair scan used where no pair bitsets exist (gm_dfs_kernel): span ends
@@ -653,7 +1020,7 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, nt = blockDim.x;
-	const int lane = tid & 31, warp = tid >> 5;
+	const int lane = tid & 31;
 	const int NS = c_par.n_searches, ND = c_par.n_descr;
 	const int W = c_par.w_winsize;
 	const int Lc = c_par.halo - W;            // context nucleotides kept on each side
@@ -664,9 +1031,8 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
 	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
 	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
-	uint32_t *sm_ent = reinterpret_cast<uint32_t *>(p);        p += (size_t)nt * GM_WL_WORDS * 4;
-	uint8_t *sm_wst = p;                                       p += (size_t)nt * c_par.win_stage;
 	uint8_t *sm_win = p;                                       p += (size_t)nt * wstride;
+	uint32_t *sm_bits = reinterpret_cast<uint32_t *>(p);       p += (size_t)nt * c_par.win_bits * 4;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
 
 	for (int i = tid; i < NS * (int)(sizeof(DevSearch) / 4); i += nt)
@@ -686,6 +1052,13 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	L.el_base = NS + c_par.frame_words;
 	uint8_t *mywin = sm_win + (size_t)tid * wstride;
 	L.sq = mywin + Lc;
+	// the lane's own pair bitsets over its window (same layout as a tile's, one
+	// strand; the lane stride is an odd number of words, so the lanes of a warp
+	// hit different banks): bit Lc + rel <-> window-relative position rel
+	PairBits mypb;
+	mypb.base = sm_bits + (size_t)tid * c_par.win_bits;
+	mypb.nwb = ((Wtot + 31) >> 5) + 3;
+	mypb.n_dups = c_par.n_dups;
 	L.szero = L.slen = L.comp = 0;
 	L.rec = 0;
 	L.seq = 0;
@@ -693,124 +1066,111 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 		unmark(L, d);
 		set_cnt(L, d, GM_UNDEF, GM_UNDEF);
 	}
-	uint32_t *went = sm_ent + (size_t)warp * 32 * GM_WL_WORDS;
-	const int wst = c_par.win_stage;          // packed bytes staged per worklist entry
-	uint8_t *wstage = sm_wst + (size_t)warp * 32 * wst;
 	__syncthreads();
 
 	const unsigned long long wl_n = min(*A.wl_count, A.wl_cap);
 	int s = 0, ph = PH_IDLE;
 	bool exhausted = false;
-	int bavail = 0, bnext = 0; // entries of the current batch not yet handed out (warp-uniform)
+	const int nwl = mypb.nwb;
+	// entries a warp takes at a time: all its idle lanes when the worklist is long;
+	// when it is short (a strong sieve) spread it over every warp of the grid --
+	// the lanes of a warp diverge, so a warp with 32 survivors runs 32 enumerations
+	// one after the other while the rest of the GPU idles
+	const unsigned long long n_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+	const int per = (int)max(1ull, min(32ull, (wl_n + n_warps - 1) / n_warps));
+	const int rmin = min(c_par.refill_min, per);
+	const unsigned long long gwarp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+	int taken = 0;
 
 	for (;;) {
 		const unsigned idle = __ballot_sync(0xffffffffu, ph == PH_IDLE);
-		if (idle) {
-			if (bavail == 0 && !exhausted) {
-				// next batch of 32 worklist entries, staged in shared memory
+		if (!exhausted && (__popc(idle) >= rmin || idle == 0xffffffffu)) {
+			// hand the idle lanes one worklist entry each.  Every lane builds its own
+			// window (one byte per nucleotide of the searched strand, reverse
+			// complement included, mk_rcmp src/rnamot.c:193-216) and its own pair
+			// bitsets straight from the packed database: a batch costs what one
+			// window costs
+			const int n = min(__popc(idle), per);
+			const int rank = __popc(idle & ((1u << lane) - 1));
+			unsigned long long mine;
+			if (per < 32) {
+				// short worklist: entry j of this warp is j * n_warps + its number, so that
+				// neighbouring starts (appended together, and expensive together) go to
+				// different warps
+				mine = (unsigned long long)(taken + rank) * n_warps + gwarp;
+				taken += n;
+				if ((unsigned long long)taken * n_warps + gwarp >= wl_n)
+					exhausted = true;
+			} else {
 				unsigned long long base = 0;
 				if (lane == 0)
-					base = atomicAdd(A.wl_head, 32ull);
+					base = atomicAdd(A.wl_head, (unsigned long long)n);
 				base = __shfl_sync(0xffffffffu, base, 0);
-				if (base >= wl_n)
+				if (base + n >= wl_n)
 					exhausted = true;
-				else {
-					bavail = (int)min((unsigned long long)32, wl_n - base);
-					bnext = 0;
-					if (lane < bavail) {
-						const uint4 *e = reinterpret_cast<const uint4 *>(A.wl + (base + lane) * GM_WL_WORDS);
-						uint4 *d = reinterpret_cast<uint4 *>(went + lane * GM_WL_WORDS);
-						const uint4 e0 = e[0], e1v = e[1];
-						d[0] = e0;
-						d[1] = e1v;
-						// stage the packed bytes under this entry's window now, all 32
-						// entries of the batch at once (one memory latency per batch)
-						const int ecomp = (int)(e0.y >> 31), eslen = (int)e0.w, eszero = (int)e1v.x;
-						const int64_t roff = A.rec_off[e0.z];
-						int c0 = max(eszero - Lc, 0), c1 = min(eszero - Lc + Wtot, eslen); // strand coords [c0, c1)
-						if (c1 < c0)
-							c1 = c0;
-						const int64_t gs = roff + (ecomp ? eslen - c1 : c0); // first forward nucleotide
-						const int64_t b16 = (gs >> 1) & ~(int64_t)15;
-						d[1].w = (uint32_t)((gs >> 1) - b16) | ((uint32_t)(gs & 1) << 8); // byte/nibble of gs in the stage
-						const uint4 *src = reinterpret_cast<const uint4 *>(A.packed + b16);
-						uint4 *dst = reinterpret_cast<uint4 *>(wstage + (size_t)lane * wst);
-						for (int k = 0; k < (wst >> 4); k++)
-							dst[k] = src[k];
-					}
-					__syncwarp();
-				}
+				mine = base + rank;
 			}
-			const int rank = __popc(idle & ((1u << lane) - 1));
-			const bool take = ph == PH_IDLE && rank < bavail;
-			const unsigned tm = __ballot_sync(0xffffffffu, take);
-			uint32_t e1 = 0, v0lo = 0, v0hi = 0;
-			if (take) {
-				const uint32_t *e = went + (bnext + rank) * GM_WL_WORDS;
-				e1 = e[1];
-				L.rec = e[2];
-				L.slen = (int)e[3];
-				L.szero = (int)e[4];
-				L.comp = (int)(e1 >> 31);
+			if (ph == PH_IDLE && rank < n && mine < wl_n) {
+				const uint4 *e = reinterpret_cast<const uint4 *>(A.wl + mine * GM_WL_WORDS);
+				const uint4 e0 = e[0], e1v = e[1];
+				L.rec = e0.z;
+				L.slen = (int)e0.w;
+				L.szero = (int)e1v.x;
+				L.comp = (int)(e0.y >> 31);
 				L.seq = 0;
-				v0lo = e[5];
-				v0hi = e[6];
-			}
-			// build the windows of the lanes that took a start, one lane at a time,
-			// all 32 lanes copying
-			const int myslot = bnext + rank; // batch slot of the entry this lane took
-			for (unsigned m = tm; m; m &= m - 1) {
-				const int j = __ffs(m) - 1;
-				const int jcomp = __shfl_sync(0xffffffffu, L.comp, j);
-				const int jslen = __shfl_sync(0xffffffffu, L.slen, j);
-				const int jszero = __shfl_sync(0xffffffffu, L.szero, j);
-				const int jslot = __shfl_sync(0xffffffffu, myslot, j);
-				const uint32_t where = went[jslot * GM_WL_WORDS + 7];
-				const int nib0 = (int)(where & 0xff) * 2 + (int)((where >> 8) & 1); // nibble index of gs
-				const uint8_t *stg = wstage + (size_t)jslot * wst;
-				uint8_t *win = sm_win + (size_t)((warp << 5) + j) * wstride;
-				const int c0 = max(jszero - Lc, 0), c1 = max(min(jszero - Lc + Wtot, jslen), c0);
-				for (int i = lane; i < Wtot; i += 32) {
-					const int c = jszero - Lc + i; // strand coordinate
-					uint8_t v = (uint8_t)(4 << 4);
-					if (c >= c0 && c < c1) {
-						// forward nucleotide gs + k lies k nibbles into the stage
-						const int k = nib0 + (jcomp ? c1 - 1 - c : c - c0);
-						const unsigned byte = stg[k >> 1];
-						v = expand_code((byte >> ((k & 1) * 4)) & 15);
-						if (jcomp)
-							v = complement_byte(v);
+				const int64_t roff = A.rec_off[L.rec];
+				const int slen = L.slen, comp = L.comp, c00 = L.szero - Lc;
+				uint32_t *mb = const_cast<uint32_t *>(mypb.base);
+				for (int w = 0; w < nwl; w++) {
+					uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+					const int i0 = w << 5;
+					for (int t = 0; t < 32 && i0 + t < Wtot; t++) {
+						const int c = c00 + i0 + t; // strand coordinate
+						uint8_t v = (uint8_t)(4 << 4);
+						if (c >= 0 && c < slen) {
+							const int64_t gf = roff + (comp ? slen - 1 - c : c);
+							const unsigned byte = A.packed[gf >> 1];
+							v = expand_code((byte >> ((gf & 1) * 4)) & 15);
+							if (comp)
+								v = complement_byte(v);
+						}
+						mywin[i0 + t] = v;
+						const int bc = bcode_of(v);
+						b0 |= (uint32_t)(bc == 0) << t;
+						b1 |= (uint32_t)(bc == 1) << t;
+						b2 |= (uint32_t)(bc == 2) << t;
+						b3 |= (uint32_t)(bc == 3) << t;
 					}
-					win[i] = v;
+					mb[0 * nwl + w] = b0;
+					mb[1 * nwl + w] = b1;
+					mb[2 * nwl + w] = b2;
+					mb[3 * nwl + w] = b3;
+					// the other tables: unions of the base bitsets
+					for (int dd = 1; dd < mypb.n_dups; dd++) {
+						const unsigned dup = c_par.dups[dd];
+#pragma unroll
+						for (int x = 0; x < 4; x++) {
+							const unsigned row = dup >> (x * 5);
+							mb[(dd * 4 + x) * nwl + w] = ((row & 1u) ? b0 : 0u) | ((row & 2u) ? b1 : 0u) |
+								((row & 4u) ? b2 : 0u) | ((row & 8u) ? b3 : 0u);
+						}
+					}
 				}
-			}
-			__syncwarp();
-			if (take) {
-				const DevSearch &S0 = sm_ds[0];
 				const int dl = min(W, L.slen - L.szero) - 1;
 				L_ZD(L, 0) = pk16(0, dl);
 				s = 0;
 				ph = PH_ENTER;
-				if ((e1 >> 30) & 1) {
-					// the prefilter already computed search 0's candidate mask
-					const int lsd = S0.minglen - 1;
-					L_FR(L, 0, 0) = pk16(lsd, lsd);   // nothing left above the chunk
-					L_FR(L, 0, 4) = pk16(0, lsd);
-					L_FR(L, 0, 5) = v0lo;
-					L_FR(L, 0, 6) = v0hi;
-					ph = PH_SPAN;
-				}
 			}
-			const int took = __popc(tm);
-			bavail -= took;
-			bnext += took;
-			if (exhausted && bavail == 0 && __all_sync(0xffffffffu, ph == PH_IDLE))
-				break;
+			__syncwarp();
 		}
-#define GM_MASK(S, z, clo, n) wc_mask_scan(L, (S), (z), (clo), (n))
+		if (exhausted && __all_sync(0xffffffffu, ph == PH_IDLE))
+			break;
+#define GM_MASK(S, z, clo, n) wc_mask(mypb, L.sq, 0, Lc, (S).dupi, (S).flt, (z), (clo), (n))
+#define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, 0, Lc, (S), (T), (s5), (s3), (hl))
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
+#undef GM_TAIL
 #undef GM_MASK
 	}
 }

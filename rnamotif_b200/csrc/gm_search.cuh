@@ -44,7 +44,7 @@ struct DevSearch {
 	int mm5;               // mismatch limit of the head (ss: used by the fused ss trip)
 	int hmm;               // helix: d or d3 has seq= with mismatch= (their counters need the
 	                       // whole extension of match_wchlx, see wx_finish_mm)
-	int pad0;
+	int dupi_t;            // index of the TRANSPOSED duplex table in DevParams::dups (reverse masks), or -1
 	int last;              // 1 for the final search (hit sink follows)
 	int fr;                // word offset of this search's frame in the lane state
 	int dupi;              // index of `duplex` in DevParams::dups (pair bitsets), or -1
@@ -54,8 +54,12 @@ struct DevSearch {
 	// the nucleotides in between; -1 if there is none
 	int kid_t, kid_off;
 	int sib_t, sib_off;
+	// tail look-ahead: the LAST helix group of this helix's interior chain (only
+	// fixed-length single strands behind it): it must end lk_off nucleotides before
+	// the interior does, so its 3' end is known as soon as this helix is chosen
+	int lk_t, lk_off;
 };
-static_assert(sizeof(DevSearch) == 29 * 4, "DevSearch is staged with an odd word stride");
+static_assert(sizeof(DevSearch) == 31 * 4, "DevSearch is staged with an odd word stride");
 
 #define GM_MAX_DUPS 8
 
@@ -70,11 +74,15 @@ struct DevParams {
 	int frame_words;        // sum of all frames
 	int win_stride;         // split path: bytes of one lane window
 	int win_stage;          // split path: packed bytes staged per worklist entry (multiple of 16)
+	int win_bits;           // split path: words of one lane's pair bitsets (odd)
 	int n_dups;             // distinct duplex tables with pair bitsets
 	unsigned dups[GM_MAX_DUPS];
 	int refill_min;         // idle lanes a warp waits for before it hands out new starts
 	int pf_search;          // search whose candidate mask is the level-0 prefilter, or -1
 	int pf_z;               // its 5' start relative to the window (fixed-length ss before it)
+	int sieve;              // level-0 sieve (sieve_word): word-parallel test of pf_search's span ends
+	int pf_deep;            // second stage behind the sieve: kid / tail look-ahead per span end
+	int sv_id;              // index in dups[] of the identity table (its bitsets are the base bitsets)
 	int lit_present;        // literal prefilter (gm_plan_t::literal): regex index, window, length
 	int lit_rx, lit_lmin, lit_lmax, lit_mm, lit_len;
 	int lite;               // plan of single strands and proper helices only: the lane

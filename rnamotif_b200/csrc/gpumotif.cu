@@ -123,22 +123,31 @@ extern "C" int gm_device_count(void)
 // kernel variants: FULL only when the plan has something besides single strands
 // and proper helices
 typedef void (*search_kernel_t)(const ScanArgs);
-static search_kernel_t fused_kernel(bool full, bool lit)
+static search_kernel_t fused_kernel(bool full, int pf)
 {
-	if (lit)
-		return full ? (search_kernel_t)gm_search_kernel<0, true, true> : (search_kernel_t)gm_search_kernel<0, false, true>;
-	return full ? (search_kernel_t)gm_search_kernel<0, true, false> : (search_kernel_t)gm_search_kernel<0, false, false>;
+	if (pf == 2)
+		return full ? (search_kernel_t)gm_search_kernel<0, true, 2> : (search_kernel_t)gm_search_kernel<0, false, 2>;
+	if (pf == 1)
+		return full ? (search_kernel_t)gm_search_kernel<0, true, 1> : (search_kernel_t)gm_search_kernel<0, false, 1>;
+	return full ? (search_kernel_t)gm_search_kernel<0, true, 0> : (search_kernel_t)gm_search_kernel<0, false, 0>;
+}
+// level-0 prefilter variant of a plan: 2 sieve, 1 literal, 0 per-start masks
+static int pf_of(const DevParams &par)
+{
+	return par.sieve ? 2 : par.lit_present ? 1 : 0;
 }
 static search_kernel_t dfs_kernel(bool full)
 {
 	return full ? (search_kernel_t)gm_dfs_kernel<true> : (search_kernel_t)gm_dfs_kernel<false>;
 }
-static search_kernel_t pre_kernel(bool lit)
+static search_kernel_t pre_kernel(int pf)
 {
-	return lit ? (search_kernel_t)gm_search_kernel<1, false, true> : (search_kernel_t)gm_search_kernel<1, false, false>;
+	return pf == 2 ? (search_kernel_t)gm_search_kernel<1, false, 2> : pf == 1 ? (search_kernel_t)gm_search_kernel<1, false, 1> : (search_kernel_t)gm_search_kernel<1, false, 0>;
 }
 
 // --------------------------------------------------------------- plan checks
+
+#define GM_WL_SEG_NT ((int64_t)16 << 20) // default segment of the split path, nucleotides
 
 static int kind_of(const gm_plan_t *pl, int d)
 {
@@ -304,7 +313,16 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	par->dminlen = pl->dminlen;
 	par->strict_helices = pl->strict_helices;
 	par->halo = W + cx + 2;
-	// frames, pair-bitset tables and span-end prefilter parameters
+	// frames, pair-bitset tables and span-end prefilter parameters.  Table 0 is
+	// always the identity: its "pair" bitsets are the base bitsets every other
+	// table's sets are derived from (load_tile) and the sieve's second operand
+	{
+		unsigned ident = 0;
+		for (int x = 0; x < 4; x++)
+			ident |= 1u << (x * 5 + x);
+		par->dups[0] = ident;
+		par->n_dups = 1;
+	}
 	int fr = 0;
 	for (int s = 0; s < NS; s++) {
 		DevSearch &S = ds[s];
@@ -339,13 +357,54 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		}
 	}
 	par->frame_words = fr;
-	// look-ahead targets (see DevSearch::kid_t / sib_t)
+	// bitsets of the transposed tables, for masks that run from a known 3' end
+	// (wc_mask_rev); wc/gu tables are symmetric and share their own bitsets
 	for (int s = 0; s < NS; s++) {
 		DevSearch &S = ds[s];
-		S.kid_t = S.sib_t = -1;
-		S.kid_off = S.sib_off = 0;
+		S.dupi_t = -1;
+		if (S.kind != K_WC || S.dupi < 0)
+			continue;
+		unsigned t = 0;
+		for (int x = 0; x < 5; x++)
+			for (int y = 0; y < 5; y++)
+				if ((S.duplex >> (x * 5 + y)) & 1u)
+					t |= 1u << (y * 5 + x);
+		int k;
+		for (k = 0; k < par->n_dups; k++)
+			if (par->dups[k] == t)
+				break;
+		if (k == par->n_dups && par->n_dups < GM_MAX_DUPS)
+			par->dups[par->n_dups++] = t;
+		if (k < par->n_dups)
+			S.dupi_t = k;
+	}
+	// look-ahead targets (see DevSearch::kid_t / sib_t / lk_t)
+	const bool no_tail = getenv("GPUMOTIF_NO_TAIL") != NULL;
+	for (int s = 0; s < NS; s++) {
+		DevSearch &S = ds[s];
+		S.kid_t = S.sib_t = S.lk_t = -1;
+		S.kid_off = S.sib_off = S.lk_off = 0;
 		if (S.kind != K_WC)
 			continue;
+		{
+			// the interior chain s+1 -> next_s -> ...: its last helix group, if only
+			// fixed-length single strands follow it
+			int chain[GM_MAX_DESCR], n = 0;
+			for (int u = s + 1; u >= 0 && u < NS && n < GM_MAX_DESCR; u = ds[u].next_s)
+				chain[n++] = u;
+			int off = 0, k = n - 1;
+			while (k >= 0 && ds[chain[k]].kind == K_SS && ds[chain[k]].minlen == ds[chain[k]].maxlen) {
+				off += ds[chain[k]].minlen;
+				k--;
+			}
+			if (k >= 0 && !no_tail) {
+				const DevSearch &T = ds[chain[k]];
+				if (T.kind == K_WC && T.dupi_t >= 0 && (T.flt & 0xff) > 0) {
+					S.lk_t = chain[k];
+					S.lk_off = off;
+				}
+			}
+		}
 		for (int which = 0; which < 2; which++) {
 			int u = which == 0 ? s + 1 : S.next_s, off = 0;
 			while (u >= 0 && u < NS && ds[u].kind == K_SS && ds[u].minlen == ds[u].maxlen &&
@@ -398,6 +457,33 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		par->lit_mm = pl->literal.mismatch;
 		par->lit_len = pl->regex[pl->literal.regex].mm_len;
 	}
+	// level-0 sieve: word-parallel version of the pf_search mask (needs the base
+	// bitsets = pair bitsets of the identity table, and a budget of at most one)
+	par->sieve = 0;
+	par->sv_id = -1;
+	if (par->pf_search >= 0 && !par->lit_present && getenv("GPUMOTIF_NO_SIEVE") == NULL) {
+		const DevSearch &SP = ds[par->pf_search];
+		const int req = SP.flt & 0xff, budget = (SP.flt >> 8) & 0xff;
+		if ((SP.kind == K_WC || SP.kind == K_QU) && req >= 1 && budget <= 1 &&
+		    SP.minglen - 1 - 2 * (req - 1) >= 1 && SP.maxglen - SP.minglen <= 160) {
+			par->sieve = 1;
+			par->sv_id = 0;
+			// look-ahead inside the sieve when the first helix has targets (themselves
+			// sievable: a budget of at most one) and few lengths to try
+			auto sievable = [&](int t) {
+				return t >= 0 && (ds[t].flt & 0xff) >= 1 && ((ds[t].flt >> 8) & 0xff) <= 1 &&
+					ds[t].minglen - 1 - 2 * ((ds[t].flt & 0xff) - 1) >= 1;
+			};
+			if (SP.kind == K_WC && SP.minlen >= 1 && SP.maxlen - SP.minlen <= 3 &&
+			    (SP.lk_t < 0 || sievable(SP.lk_t)) && (SP.kid_t < 0 || sievable(SP.kid_t)) &&
+			    (SP.lk_t >= 0 || SP.kid_t >= 0) && getenv("GPUMOTIF_NO_DEEP") == NULL)
+				par->pf_deep = 1;
+			// ... and the helix that follows the first interior helix, if its place is known
+			if (par->pf_deep && SP.kid_t >= 0 && ds[SP.kid_t].sib_t >= 0 && sievable(ds[SP.kid_t].sib_t) &&
+			    getenv("GPUMOTIF_NO_DEEP2") == NULL)
+				par->pf_deep = 2;
+		}
+	}
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
 		if ((ds[s].kind != K_SS && ds[s].kind != K_WC) || ds[s].hmm)
@@ -435,12 +521,13 @@ extern "C" int gm_plan_check(const gm_plan_t *plan)
 static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state = true)
 {
 	// mirrors the carve-up at the top of gm_search_kernel
-	const int Lb = (tile + 2 * c->par.halo + 15) & ~15;
+	const int Lb = (tile + 2 * c->par.halo + 31) & ~31;
 	const size_t stage = ((Lb >> 1) + 32 + 15) & ~15;
 	const size_t pb = (((size_t)2 * c->par.n_dups * 4 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15;
 	const size_t lit = c->par.lit_present ? (((size_t)2 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15 : 0;
 	const size_t buf_bytes = 2 * (size_t)Lb + pb + (GM_REC_CACHE + 2) * 8 + lit;
-	const size_t warp_bytes = 16 + stage + (with_state ? 2 : 1) * buf_bytes + GM_QCAP * 2;
+	const size_t warp_bytes = 16 + stage + (with_state ? 2 : 1) * buf_bytes + GM_QCAP * 2 +
+		(c->par.sieve ? ((6 * (size_t)(((Lb + 31) >> 5) + 4) * 4 + 15) & ~(size_t)15) : 0);
 	size_t n = 0;
 	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
 	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
@@ -458,9 +545,8 @@ static size_t dfs_smem_need(const gm_ctx *c, int threads)
 	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
 	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
 	n += (c->par.n_descr * 4 + 15) & ~15;
-	n += (size_t)threads * GM_WL_WORDS * 4;
-	n += (size_t)threads * c->par.win_stage;
 	n += (size_t)threads * c->par.win_stride;
+	n += (size_t)threads * c->par.win_bits * 4;
 	n += (size_t)c->par.words_per_lane * threads * 4;
 	return n;
 }
@@ -473,8 +559,8 @@ static int warps_per_sm(gm_ctx *c, int threads, int tile)
 	if (need + 1024 > 227 * 1024)
 		return 0;
 	int n = 0;
-	if (cudaFuncSetAttribute(fused_kernel(c->full, c->par.lit_present != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
-	    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel(c->full, c->par.lit_present != 0), threads, need) != cudaSuccess) {
+	if (cudaFuncSetAttribute(fused_kernel(c->full, pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
+	    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel(c->full, pf_of(c->par)), threads, need) != cudaSuccess) {
 		cudaGetLastError();
 		return 0;
 	}
@@ -503,6 +589,7 @@ static int auto_tile(gm_ctx *c)
 
 static int configure_launch(gm_ctx *c, int tile)
 {
+	const int tile_arg = tile;
 	if (tile <= 0)
 		tile = auto_tile(c);
 	// warps are independent (private tile buffers), so small blocks cost nothing
@@ -526,9 +613,9 @@ static int configure_launch(gm_ctx *c, int tile)
 	c->threads = best_t;
 	c->par.tile = tile;
 	c->smem_bytes = smem_need(c, best_t, tile);
-	CU(cudaFuncSetAttribute(fused_kernel(c->full, c->par.lit_present != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+	CU(cudaFuncSetAttribute(fused_kernel(c->full, pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
 	int per_sm = 0;
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel(c->full, c->par.lit_present != 0), c->threads, c->smem_bytes));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel(c->full, pf_of(c->par)), c->threads, c->smem_bytes));
 	if (per_sm < 1)
 		return fail("search kernel does not fit on an SM (threads %d, smem %zu)", c->threads, c->smem_bytes);
 	c->blocks = per_sm * c->n_sm;
@@ -545,17 +632,37 @@ static int configure_launch(gm_ctx *c, int tile)
 		words++;
 	c->par.win_stride = words * 4;
 	c->par.win_stage = (((wtot + 1) / 2 + 1 + 15 + 15) & ~15);
+	c->par.win_bits = (c->par.n_dups * 4 * (((wtot + 31) >> 5) + 3)) | 1;
 	bool eligible = wtot <= 512 &&
 		(c->par.pf_search >= 0 || c->par.lit_present ||
 		 (S0.rx5 >= 0 && S0.mm5 == 0 && !c->plan.regex[S0.rx5].eol));
-	// The fused kernel is the default: on the measured configurations it is the
-	// faster of the two (profiles/README.md).  GPUMOTIF_PATH=split selects the
-	// worklist pair, =fused forces the single kernel.
+	// Which path: the worklist pair (sieve / prefilter kernel -> DFS kernel with
+	// per-lane windows) wins where the level-0 filter is strong, because the small
+	// filter kernel then runs out of the instruction cache and the few survivors are
+	// enumerated 32 to a warp; elsewhere the fused kernel does (profiles/README.md).
+	// GPUMOTIF_PATH=split / =fused overrides.
 	const char *force = getenv("GPUMOTIF_PATH");
-	if (force == NULL || strcmp(force, "split") != 0)
+	if (force != NULL && strcmp(force, "split") == 0)
+		eligible = wtot <= 512;
+	else if (force != NULL && strcmp(force, "fused") == 0)
 		eligible = false;
-	else if (wtot <= 512)
-		eligible = true;
+	else
+		eligible = wtot <= 512 && ((c->par.sieve && c->par.pf_deep) || (c->par.lit_present && c->full));
+	const int fused_tile0 = c->par.tile;
+	if (eligible && tile_arg <= 0 && c->par.sieve) {
+		// the sieve kernel keeps one tile buffer and no lane state: take a large tile
+		// (less halo per start) whose sieve words fill whole passes of 32 lanes
+		for (int t2 = 1984; t2 >= 448; t2 = t2 == 1984 ? 960 : 448) {
+			if (smem_need(c, 256, t2, false) * 2 + 2048 <= smem_sm) {
+				tile = t2;
+				break;
+			}
+			if (t2 == 448)
+				break;
+		}
+		c->par.tile = tile;
+	}
+	const int fused_tile = fused_tile0;
 	c->use_split = false;
 	if (eligible) {
 		c->a_threads = 256;
@@ -580,15 +687,20 @@ static int configure_launch(gm_ctx *c, int tile)
 		cudaGetLastError();
 		int na = 0;
 		if (c->b_threads > 0 && c->a_smem <= smem_sm &&
-		    cudaFuncSetAttribute(pre_kernel(c->par.lit_present != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
+		    cudaFuncSetAttribute(pre_kernel(pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
 		    cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->b_smem) == cudaSuccess &&
-		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(c->par.lit_present != 0), c->a_threads, c->a_smem) == cudaSuccess &&
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(pf_of(c->par)), c->a_threads, c->a_smem) == cudaSuccess &&
 		    na >= 1) {
 			c->a_blocks = na * c->n_sm;
 			c->use_split = true;
 		}
 		cudaGetLastError();
 	}
+	if (!c->use_split)
+		c->par.tile = fused_tile; // the split path's larger tile may not fit the fused kernel
+	if (getenv("GPUMOTIF_DEBUG") != NULL && c->use_split)
+		fprintf(stderr, "gpumotif: split path, tile %d, sieve/prefilter %d x %d (%zu B), dfs %d x %d (%zu B)\n", c->par.tile,
+			c->a_blocks, c->a_threads, c->a_smem, c->b_blocks, c->b_threads, c->b_smem);
 	CU(cudaMemcpyToSymbolAsync(c_par, &c->par, sizeof c->par, 0, cudaMemcpyHostToDevice, c->stream));
 	if (c->device < 64 && g_const_owner[c->device] != c)
 		g_const_owner[c->device] = NULL; // force a full re-bind of the __constant__ plan at the next launch
@@ -617,7 +729,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->wl_cap = 0;
 	c->h_raw = NULL;
 	c->h_raw_cap = 0;
-	c->seg_nt = (int64_t)16 << 20;
+	c->seg_nt = GM_WL_SEG_NT;
 	c->use_split = false;
 	c->chars_cap = c->packed_cap = c->rec_cap = 0;
 	c->total_nt = 0;
@@ -1046,7 +1158,7 @@ static int launch(gm_ctx *c)
 			A.n_tiles = (hi - lo + c->par.tile - 1) / c->par.tile;
 			A.tile_counter = c->d_counters + 8 + i;
 			int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
-			fused_kernel(c->full, c->par.lit_present != 0)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+			fused_kernel(c->full, pf_of(c->par))<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 			CU(cudaGetLastError());
 			c->stats.n_launches++;
 			lo = hi;
@@ -1055,15 +1167,21 @@ static int launch(gm_ctx *c)
 		if (n_chunks > 0)
 			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
 		int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
-		fused_kernel(c->full, c->par.lit_present != 0)<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
+		fused_kernel(c->full, pf_of(c->par))<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 		CU(cudaGetLastError());
 		c->stats.n_launches++;
 	} else if (A.n_tiles > 0) {
 		if (n_chunks > 0)
 			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
 		// split path, one (prefilter, dfs) launch pair per segment of the range
+		// The worklist holds GM_WL_SEG_NT x 2 entries: enough for every start of a
+		// default segment.  Segments grow beyond that when the previous scans showed
+		// that few starts survive the filter (fewer launches, and the DFS kernel's
+		// tail -- a handful of long enumerations -- is paid once per segment); if a
+		// segment then overflows after all, the scan is repeated with default
+		// segments (gm_scan_finish), nothing is lost.
+		const size_t need = (size_t)GM_WL_SEG_NT * 2;
 		const int64_t seg = std::min<int64_t>(c->seg_nt, c->p_end - c->p_begin);
-		const size_t need = (size_t)seg * c->p_strands;
 		if (c->d_wl == NULL || c->wl_cap < need) {
 			cudaFree(c->d_wl);
 			c->d_wl = NULL;
@@ -1080,7 +1198,7 @@ static int launch(gm_ctx *c)
 			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
 			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
 			int ablocks = (int)std::min<int64_t>(c->a_blocks, A.n_tiles);
-			pre_kernel(c->par.lit_present != 0)<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
+			pre_kernel(pf_of(c->par))<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
 			dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
@@ -1129,7 +1247,7 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 		return fail("no scan in flight");
 	c->pending = false;
 	CU(cudaSetDevice(c->device));
-	unsigned long long cnt[4];
+	unsigned long long cnt[8];
 	for (;;) {
 		CU(cudaMemcpyAsync(cnt, c->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
@@ -1141,6 +1259,28 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 			c->stats.pack_ms = 0;
 		}
 		cudaGetLastError();
+		if (getenv("GPUMOTIF_DEBUG") != NULL)
+			fprintf(stderr, "gpumotif: hits %llu, starts %llu, worklist (last segment) %llu, machine entries %llu\n",
+				cnt[1], cnt[2], cnt[3], cnt[5]);
+		if (c->use_split && cnt[7]) {
+			// a grown segment overflowed the worklist: repeat with default segments
+			if (c->seg_nt <= GM_WL_SEG_NT)
+				return fail("worklist overflow with default segments (internal error)");
+			c->seg_nt = GM_WL_SEG_NT;
+			c->stats.n_retries++;
+			if (launch(c))
+				return -1;
+			continue;
+		}
+		if (c->use_split && c->p_end > c->p_begin) {
+			// survivors per start of this scan -> segment size of the next one, so that
+			// a segment fills at most a quarter of the worklist
+			const double rate = (double)cnt[6] / ((double)(c->p_end - c->p_begin) * c->p_strands);
+			const double cap = (double)GM_WL_SEG_NT * 2;
+			double seg = rate > 0 ? 0.25 * cap / (rate * c->p_strands) : 1e18;
+			seg = std::max<double>((double)GM_WL_SEG_NT, std::min<double>(seg, (double)((int64_t)1 << 30)));
+			c->seg_nt = (int64_t)seg / GM_WL_SEG_NT * GM_WL_SEG_NT;
+		}
 		if (cnt[1] <= c->hit_cap)
 			break;
 		// the hit buffer was too small: nothing is lost, run again with room
@@ -1193,6 +1333,29 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	c->stats.d2h_bytes = n * sw * 4 + sizeof cnt;
 	c->stats.n_hits = n;
 	c->stats.n_starts = cnt[2];
+	if (c->par.sieve) {
+		// the sieve does not visit the starts one by one: count them here
+		// (RM_find_motif searches szero in [0, slen - rm_dminlen], src/find_motif.c:184-205)
+		uint64_t ns = 0;
+		for (size_t r = 0; r + 1 < c->rec_off.size(); r++) {
+			const int64_t lo = std::max(c->rec_off[r], c->p_begin);
+			const int64_t hi = std::min(c->rec_off[r + 1], c->p_end);
+			if (hi <= lo)
+				continue;
+			// forward strand: position pos is a start if slen - pos >= dminlen; the
+			// complementary strand maps pos to szero = slen - 1 - pos
+			const int64_t off = c->rec_off[r], slen = c->rec_off[r + 1] - off, dm = c->par.dminlen;
+			const int64_t f_hi = std::min(hi, off + slen - dm + 1);
+			if (f_hi > lo)
+				ns += (uint64_t)(f_hi - lo);
+			if (c->p_strands > 1) {
+				const int64_t c_lo = std::max(lo, off + dm - 1);
+				if (hi > c_lo)
+					ns += (uint64_t)(hi - c_lo);
+			}
+		}
+		c->stats.n_starts = ns;
+	}
 	// strand-nt in range = nucleotides in range x strands
 	c->stats.n_strand_nt = (uint64_t)(c->p_end - c->p_begin) * (uint64_t)c->p_strands;
 	return 0;
