@@ -1171,9 +1171,13 @@ static int launch(gm_ctx *c)
 		CU(cudaGetLastError());
 		c->stats.n_launches++;
 	} else if (A.n_tiles > 0) {
-		if (n_chunks > 0)
+		// split path, one (prefilter, dfs) launch pair per segment of the range.
+		// On the first scan of a fresh chunked upload a segment ends where its
+		// chunk's data end (less the halo a tile reads ahead) and waits for that
+		// chunk only, so the search of chunk i overlaps the copy of chunk i+1.
+		const bool stream_in = c->upload_fresh && n_chunks > 1 && n_chunks <= 16;
+		if (n_chunks > 0 && !stream_in)
 			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
-		// split path, one (prefilter, dfs) launch pair per segment of the range
 		// The worklist holds GM_WL_SEG_NT x 2 entries: enough for every start of a
 		// default segment.  Segments grow beyond that when the previous scans showed
 		// that few starts survive the filter (fewer launches, and the DFS kernel's
@@ -1190,9 +1194,18 @@ static int launch(gm_ctx *c)
 		}
 		A.wl = c->d_wl;
 		A.wl_cap = c->wl_cap;
-		for (int64_t g0 = c->p_begin; g0 < c->p_end; g0 += seg) {
+		int ci = 0;
+		for (int64_t g0 = c->p_begin; g0 < c->p_end; g0 = A.g_end) {
 			A.g_begin = g0;
 			A.g_end = std::min<int64_t>(g0 + seg, c->p_end);
+			if (stream_in) {
+				const int64_t slack = (int64_t)c->par.halo + c->par.tile;
+				while (ci < n_chunks - 1 && c->chunk_end[ci] - slack <= g0)
+					ci++;
+				CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[ci], 0));
+				if (ci < n_chunks - 1)
+					A.g_end = std::min<int64_t>(A.g_end, c->chunk_end[ci] - slack);
+			}
 			A.n_tiles = (A.g_end - A.g_begin + c->par.tile - 1) / c->par.tile;
 			// tile counter, worklist count and head restart for every segment
 			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
