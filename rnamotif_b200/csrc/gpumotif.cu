@@ -17,6 +17,8 @@
 #include <numeric>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "gpumotif.h"
 #include "gm_machine.cuh"
 #include "gm_fastn.cuh"
@@ -99,6 +101,13 @@ struct gm_ctx {
 	uint32_t *h_raw;               // pinned staging for the device -> host gather
 	size_t h_raw_cap;              // words
 	std::vector<uint64_t> keys;    // sort keys, reused
+	// device-side ordering of the candidates (gm_scan_finish)
+	void *d_sort;                  // keys in/out, indices in/out, cub temp storage
+	size_t sort_cap;
+	uint32_t *d_sorted;            // the candidates in enumeration order
+	size_t sorted_cap;
+	bool dev_sorted;               // the last scan was ordered on the device
+	const uint32_t *hits_view;     // what gm_hits() hands out
 	size_t n_hits;
 	gm_scan_stats_t stats;
 	// pending launch
@@ -729,6 +738,12 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->wl_cap = 0;
 	c->h_raw = NULL;
 	c->h_raw_cap = 0;
+	c->d_sort = NULL;
+	c->sort_cap = 0;
+	c->d_sorted = NULL;
+	c->sorted_cap = 0;
+	c->dev_sorted = false;
+	c->hits_view = NULL;
 	c->seg_nt = GM_WL_SEG_NT;
 	c->use_split = false;
 	c->chars_cap = c->packed_cap = c->rec_cap = 0;
@@ -831,6 +846,8 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 	cudaFree(c->d_hits);
 	cudaFree(c->d_wl);
 	cudaFreeHost(c->h_raw);
+	cudaFree(c->d_sort);
+	cudaFree(c->d_sorted);
 	for (int i = 0; i < 6; i++)
 		if (c->ev[i])
 			cudaEventDestroy(c->ev[i]);
@@ -1252,6 +1269,33 @@ struct HitKey {
 	uint32_t idx;
 };
 
+// ---- ordering the candidates on the device --------------------------------
+// Enumeration order = (record, strand, start, DFS rank).  A start is enumerated
+// by one lane of one launch and its candidates are appended one after the
+// other, so among equal (record, strand, start) the buffer order already is the
+// DFS rank: a STABLE sort by that 64-bit key is enough (radix sort is stable).
+__global__ void gm_sortkey_kernel(const uint32_t *__restrict__ hits, unsigned long long n, int sw,
+	unsigned long long *__restrict__ keys, uint32_t *__restrict__ idx)
+{
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+	     i += (unsigned long long)gridDim.x * blockDim.x) {
+		const uint32_t *h = hits + i * sw;
+		keys[i] = ((unsigned long long)h[0] << 32) | ((unsigned long long)(h[3] & 1) << 31) |
+			(unsigned long long)(h[1] & 0x7fffffffu);
+		idx[i] = (uint32_t)i;
+	}
+}
+__global__ void gm_gather_kernel(const uint32_t *__restrict__ hits, const uint32_t *__restrict__ idx,
+	unsigned long long n, int sw, uint32_t *__restrict__ out)
+{
+	const unsigned long long total = n * sw;
+	for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < total;
+	     k += (unsigned long long)gridDim.x * blockDim.x) {
+		const unsigned long long i = k / sw;
+		out[k] = hits[(unsigned long long)idx[i] * sw + (k - i * sw)];
+	}
+}
+
 extern "C" int gm_scan_finish(gm_ctx *c)
 {
 	if (c == NULL)
@@ -1320,9 +1364,40 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	}
 	const uint32_t *raw = c->h_raw;
 	auto t0 = std::chrono::steady_clock::now();
+	auto t1 = t0, t2 = t0;
+	c->dev_sorted = n > 0 && n < 0xffffffffull && n * sw * 4 <= ((size_t)2 << 30) && getenv("GPUMOTIF_HOST_SORT") == NULL;
+	if (c->dev_sorted) {
+		// stable radix sort of (key, buffer index) on the device, gather, one copy
+		size_t temp = 0;
+		cub::DeviceRadixSort::SortPairs(NULL, temp, (unsigned long long *)NULL, (unsigned long long *)NULL,
+			(uint32_t *)NULL, (uint32_t *)NULL, (unsigned long long)n, 0, 64, c->stream);
+		const size_t k_bytes = (n * 8 + 255) & ~(size_t)255, i_bytes = (n * 4 + 255) & ~(size_t)255;
+		if (ensure(&c->d_sort, &c->sort_cap, 2 * k_bytes + 2 * i_bytes + temp + 256))
+			return -1;
+		size_t sorted_bytes = c->sorted_cap;
+		if (ensure((void **)&c->d_sorted, &sorted_bytes, n * sw * 4))
+			return -1;
+		c->sorted_cap = sorted_bytes;
+		uint8_t *b = (uint8_t *)c->d_sort;
+		unsigned long long *k_in = (unsigned long long *)b, *k_out = (unsigned long long *)(b + k_bytes);
+		uint32_t *i_in = (uint32_t *)(b + 2 * k_bytes), *i_out = (uint32_t *)(b + 2 * k_bytes + i_bytes);
+		void *d_temp = b + 2 * k_bytes + 2 * i_bytes;
+		const int blocks = (int)std::min<size_t>((n * sw + 255) / 256, (size_t)c->n_sm * 16);
+		gm_sortkey_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hits, n, (int)sw, k_in, i_in);
+		CU(cudaGetLastError());
+		CU(cub::DeviceRadixSort::SortPairs(d_temp, temp, k_in, k_out, i_in, i_out, (unsigned long long)n, 0, 64, c->stream));
+		gm_gather_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hits, i_out, n, (int)sw, c->d_sorted);
+		CU(cudaGetLastError());
+		CU(cudaStreamSynchronize(c->stream));
+		t1 = std::chrono::steady_clock::now();
+		CU(cudaMemcpy(c->h_raw, c->d_sorted, n * sw * 4, cudaMemcpyDeviceToHost));
+		t2 = std::chrono::steady_clock::now();
+		c->hits_view = c->h_raw;
+		// (sort_ms = device ordering, d2h_ms = the copy; swapped below)
+	} else {
 	if (n > 0)
 		CU(cudaMemcpy(c->h_raw, c->d_hits, n * sw * 4, cudaMemcpyDeviceToHost));
-	auto t1 = std::chrono::steady_clock::now();
+	t1 = std::chrono::steady_clock::now();
 	// enumeration order: record, strand, start, DFS rank.  Two 64-bit keys per
 	// hit: (rec, comp, szero) and (seq, index into the gathered array)
 	std::vector<uint64_t> &keys = c->keys;
@@ -1339,10 +1414,17 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 		c->hits.resize(n * sw + n * sw / 4);
 	for (size_t i = 0; i < n; i++)
 		memcpy(&c->hits[i * sw], &raw[(size_t)(uint32_t)kp[i].b * sw], sw * 4);
-	auto t2 = std::chrono::steady_clock::now();
+	t2 = std::chrono::steady_clock::now();
+	c->hits_view = c->hits.data();
+	}
 	c->n_hits = n;
-	c->stats.d2h_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-	c->stats.sort_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+	if (c->dev_sorted) {
+		c->stats.sort_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+		c->stats.d2h_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+	} else {
+		c->stats.d2h_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+		c->stats.sort_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+	}
 	c->stats.d2h_bytes = n * sw * 4 + sizeof cnt;
 	c->stats.n_hits = n;
 	c->stats.n_starts = cnt[2];
@@ -1386,7 +1468,7 @@ extern "C" int gm_hits(const gm_ctx *c, const void **hits, size_t *n, size_t *st
 	if (c == NULL)
 		return fail("ctx is NULL");
 	if (hits)
-		*hits = c->hits.data();
+		*hits = c->hits_view;
 	if (n)
 		*n = c->n_hits;
 	if (stride)
@@ -1421,7 +1503,7 @@ extern "C" int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, 
 	}
 	if (n > 0) {
 		const int blocks = (int)std::min<size_t>(n, (size_t)c->n_sm * 32);
-		gm_window_kernel<<<blocks, 128, 0, c->stream>>>(c->d_seq_chars, c->d_rec_off, c->d_hits, n, c->stride_words,
+		gm_window_kernel<<<blocks, 128, 0, c->stream>>>(c->d_seq_chars, c->d_rec_off, c->dev_sorted ? c->d_sorted : c->d_hits, n, c->stride_words,
 			lead, wlen, c->d_win);
 		CU(cudaGetLastError());
 		CU(cudaMemcpyAsync(c->h_win, c->d_win, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -1431,8 +1513,11 @@ extern "C" int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, 
 	// order in the keys
 	if (c->wins.size() < bytes)
 		c->wins.resize(bytes + bytes / 4);
-	for (size_t i = 0; i < n; i++)
-		memcpy(&c->wins[i * wlen], c->h_win + (size_t)(uint32_t)c->keys[2 * i + 1] * wlen, wlen);
+	if (c->dev_sorted)
+		memcpy(c->wins.data(), c->h_win, bytes); // already in gm_hits() order
+	else
+		for (size_t i = 0; i < n; i++)
+			memcpy(&c->wins[i * wlen], c->h_win + (size_t)(uint32_t)c->keys[2 * i + 1] * wlen, wlen);
 	c->stats.d2h_bytes += bytes;
 	if (win)
 		*win = reinterpret_cast<const char *>(c->wins.data());
