@@ -226,20 +226,24 @@ def run_gpu_arm(args):
 
     # ---- resident leg -------------------------------------------------------
     ms.set_device_chars(d_chars.data_ptr(), rec_off)
-    kernel_ms, launches, hits_n = [], 0, 0
+    kernel_ms, filter_ms, launches, hits_n, filter_launches, survivors = [], [], 0, 0, 0, 0
 
     def step_resident():
-        nonlocal launches, hits_n
+        nonlocal launches, hits_n, filter_launches, survivors
         ms.scan(0, total, strands, copy=False)
         st = ms.stats()
         kernel_ms.append(st.kernel_ms)
+        filter_ms.append(st.filter_ms)
         launches += st.n_launches
+        filter_launches += st.n_filter_launches
+        survivors = st.n_survivors
         hits_n = st.n_hits
 
     for _ in range(args.warmup):
         step_resident()
     kernel_ms.clear()
-    launches = 0
+    filter_ms.clear()
+    launches = filter_launches = 0
     sampler = ClockSampler(local)
     sampler.start()
     t_res = timed(step_resident, args.steps)
@@ -272,10 +276,24 @@ def run_gpu_arm(args):
 
     if rank == 0:
         pk, which = peaks()
-        # algorithmic HBM traffic of the search kernel: the packed database is read
-        # once for both strands (0.5 B per nt) + the candidates written
-        alg_bytes = total * 0.5 + hits_n * (32 + 8 * ms.n_descr)
-        achieved = alg_bytes / (k_ms / 1e3) / 1e9
+        # The dominant kernel.  On the worklist path (strong level-0 filter, e.g. trna)
+        # it is the sieve kernel gm_search_kernel<1,*,2>: it alone reads the packed
+        # database (0.5 B per nt, once for both strands) and writes the worklist; the
+        # enumeration kernel gm_dfs_kernel touches only the survivors' windows.  On the
+        # fused path one kernel does both.  Its average launch duration comes from CUDA
+        # events the library records around every launch on its stream.
+        split = filter_launches > 0
+        if split:
+            dom_name = "gm_search_kernel<1,FULL,PF> (level-0 sieve / prefilter)"
+            dom_ms = float(np.sum(filter_ms)) / filter_launches            # per launch
+            per_launch_nt = total * args.steps / filter_launches
+            alg_bytes = per_launch_nt * 0.5 + survivors / max(filter_launches / args.steps, 1) * 32
+        else:
+            dom_name = "gm_search_kernel<0,FULL,PF> (fused filter + enumeration)"
+            dom_ms = k_ms / max(gpu_launches / args.steps, 1)
+            per_launch_nt = total * args.steps / max(gpu_launches, 1)
+            alg_bytes = per_launch_nt * 0.5 + hits_n * (32 + 8 * ms.n_descr) / max(gpu_launches / args.steps, 1)
+        achieved = alg_bytes / (dom_ms / 1e3) / 1e9
         traffic = None
         tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tj):
@@ -285,8 +303,9 @@ def run_gpu_arm(args):
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": alg_bytes,
                 "peak_source": which,
-                "kernel": "gm_search_kernel", "kernel_ms": k_ms,
-                "note": "the search is integer-issue bound, not HBM bound (SURVEY.md F8); see issue"}
+                "kernel": dom_name, "kernel_ms": dom_ms, "kernel_share_of_step": (float(np.sum(filter_ms)) if split else float(np.sum(kernel_ms))) / t_res,
+                "all_kernels_ms_per_step": k_ms,
+                "note": "the search is integer-issue bound, not HBM bound (SURVEY.md F8); see issue and profiles/"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_res / args.steps, "higher_is_better": True,
@@ -316,7 +335,10 @@ def run_gpu_arm(args):
                 line["issue"] = {"pair_evals_per_strand_nt": W,
                                  "pair_evals_per_s": W * total * strands / (k_ms / 1e3),
                                  "int_lane_peak_per_s": lane_peak,
-                                 "frac_of_lane_peak": W * total * strands / (k_ms / 1e3) / lane_peak}
+                                 "frac_of_lane_peak": W * total * strands / (k_ms / 1e3) / lane_peak,
+                                 "note": "the reference's pair-rule evaluations per strand-nt (oracle count) x measured "
+                                         "strand-nt/s; the sieve does the same tests 32 starts to a word, so this is "
+                                         "the algorithm-level rate, not an instruction count"}
             except Exception as e:
                 line["issue"] = {"error": str(e)}
         print(json.dumps(line), flush=True)

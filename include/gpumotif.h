@@ -57,6 +57,11 @@ typedef struct gm_scan_stats {
 	uint32_t n_launches;     /* kernels launched by the last gm_scan */
 	uint32_t n_retries;      /* re-runs because the hit buffer was too small */
 	uint64_t h2d_bytes, d2h_bytes;
+	/* worklist path (strong level-0 filter): the sieve / prefilter kernel on its own */
+	double   filter_ms;      /* sum over its launches, CUDA events around each */
+	uint64_t n_survivors;    /* starts it handed to the enumeration kernel */
+	uint32_t n_filter_launches;
+	uint32_t pad_;
 } gm_scan_stats_t;
 
 const char *gm_last_error(void);

@@ -107,6 +107,8 @@ struct gm_ctx {
 	uint32_t *d_sorted;            // the candidates in enumeration order
 	size_t sorted_cap;
 	bool dev_sorted;               // the last scan was ordered on the device
+	std::vector<cudaEvent_t> seg_ev; // split path: (before, after) the filter kernel of every segment
+	int n_seg_ev;                  // pairs recorded by the last launch
 	const uint32_t *hits_view;     // what gm_hits() hands out
 	size_t n_hits;
 	gm_scan_stats_t stats;
@@ -744,6 +746,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->sorted_cap = 0;
 	c->dev_sorted = false;
 	c->hits_view = NULL;
+	c->n_seg_ev = 0;
 	c->seg_nt = GM_WL_SEG_NT;
 	c->use_split = false;
 	c->chars_cap = c->packed_cap = c->rec_cap = 0;
@@ -926,9 +929,9 @@ static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src
 		return -1;
 	if (h_chars != NULL && ensure((void **)&c->d_chars, &c->chars_cap, (size_t)n + 64))
 		return -1;
-	// chunk size: at least 64 Mnt, at most 4 chunks (every chunk costs a kernel
+	// chunk size: at least 64 Mnt, at most 8 chunks (every chunk costs a kernel
 	// launch with its own ramp and tail), a multiple of 16 nucleotides
-	int64_t chunk = std::max<int64_t>((int64_t)64 << 20, (n + 3) / 4);
+	int64_t chunk = std::max<int64_t>((int64_t)64 << 20, (n + 7) / 8);
 	chunk = (chunk + 15) & ~(int64_t)15;
 	const int n_chunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
 	while ((int)c->chunk_ev.size() < n_chunks) {
@@ -1153,6 +1156,7 @@ static int launch(gm_ctx *c)
 	A.wl_head = c->d_counters + 4;
 	A.wl_cap = 0;
 	CU(cudaEventRecord(c->ev[3], c->stream));
+	c->n_seg_ev = 0;
 	const int n_chunks = (int)c->chunk_end.size();
 	if (A.n_tiles > 0 && !c->use_split && c->upload_fresh && n_chunks > 1 && n_chunks <= 16) {
 		// first scan of a fresh upload: one launch per chunk, each gated on its
@@ -1228,8 +1232,16 @@ static int launch(gm_ctx *c)
 			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
 			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
 			int ablocks = (int)std::min<int64_t>(c->a_blocks, A.n_tiles);
+			while ((int)c->seg_ev.size() < 2 * (c->n_seg_ev + 1)) {
+				cudaEvent_t e;
+				CU(cudaEventCreate(&e));
+				c->seg_ev.push_back(e);
+			}
+			CU(cudaEventRecord(c->seg_ev[2 * c->n_seg_ev], c->stream));
 			pre_kernel(pf_of(c->par))<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
+			CU(cudaEventRecord(c->seg_ev[2 * c->n_seg_ev + 1], c->stream));
+			c->n_seg_ev++;
 			dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
 			c->stats.n_launches += 2;
@@ -1258,6 +1270,9 @@ extern "C" int gm_scan_launch(gm_ctx *c, int64_t g_begin, int64_t g_end, int str
 	c->stats.n_launches = 0;
 	c->stats.n_retries = 0;
 	c->stats.kernel_ms = 0;
+	c->stats.filter_ms = 0;
+	c->stats.n_survivors = 0;
+	c->stats.n_filter_launches = 0;
 	if (launch(c))
 		return -1;
 	c->pending = true;
@@ -1311,6 +1326,13 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 		float ms = 0;
 		cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]);
 		c->stats.kernel_ms += ms;
+		for (int i = 0; i < c->n_seg_ev; i++) {
+			float f = 0;
+			if (cudaEventElapsedTime(&f, c->seg_ev[2 * i], c->seg_ev[2 * i + 1]) == cudaSuccess)
+				c->stats.filter_ms += f;
+		}
+		c->stats.n_filter_launches += (uint32_t)c->n_seg_ev;
+		c->stats.n_survivors += cnt[6];
 		if (cudaEventQuery(c->up_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->up_ev[0], c->up_ev[1]) == cudaSuccess) {
 			c->stats.h2d_ms = ms;   // copy + pack of the last upload, as enqueued on the copy stream
 			c->stats.pack_ms = 0;

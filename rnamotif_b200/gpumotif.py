@@ -23,7 +23,9 @@ class ScanStats(C.Structure):
                 ("d2h_ms", C.c_double), ("sort_ms", C.c_double),
                 ("n_starts", C.c_uint64), ("n_strand_nt", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_launches", C.c_uint32), ("n_retries", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("filter_ms", C.c_double), ("n_survivors", C.c_uint64),
+                ("n_filter_launches", C.c_uint32), ("pad_", C.c_uint32)]
 
 
 class GpuMotifError(RuntimeError):
