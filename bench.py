@@ -283,12 +283,23 @@ def run_gpu_arm(args):
         # fused path one kernel does both.  Its average launch duration comes from CUDA
         # events the library records around every launch on its stream.
         split = filter_launches > 0
-        if split:
+        if split and float(np.sum(filter_ms)) < 0.5 * float(np.sum(kernel_ms)):
+            # worklist path whose enumeration kernel dominates (weak filters: pk1, trna.general)
+            dom_name = "gm_dfs_kernel<FULL> (enumeration of the filter's survivors)"
+            dom_ms = (float(np.sum(kernel_ms)) - float(np.sum(filter_ms))) / filter_launches
+            per_launch_nt = total * args.steps / filter_launches
+            alg_bytes = survivors / max(filter_launches / args.steps, 1) * (32 + 64) + \
+                hits_n * (32 + 8 * ms.n_descr) / max(filter_launches / args.steps, 1)
+            split = False
+            filter_share = (float(np.sum(kernel_ms)) - float(np.sum(filter_ms))) / t_res
+        elif split:
+            filter_share = float(np.sum(filter_ms)) / t_res
             dom_name = "gm_search_kernel<1,FULL,PF> (level-0 sieve / prefilter)"
             dom_ms = float(np.sum(filter_ms)) / filter_launches            # per launch
             per_launch_nt = total * args.steps / filter_launches
             alg_bytes = per_launch_nt * 0.5 + survivors / max(filter_launches / args.steps, 1) * 32
         else:
+            filter_share = float(np.sum(kernel_ms)) / t_res
             dom_name = "gm_search_kernel<0,FULL,PF> (fused filter + enumeration)"
             dom_ms = k_ms / max(gpu_launches / args.steps, 1)
             per_launch_nt = total * args.steps / max(gpu_launches, 1)
@@ -303,7 +314,7 @@ def run_gpu_arm(args):
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": alg_bytes,
                 "peak_source": which,
-                "kernel": dom_name, "kernel_ms": dom_ms, "kernel_share_of_step": (float(np.sum(filter_ms)) if split else float(np.sum(kernel_ms))) / t_res,
+                "kernel": dom_name, "kernel_ms": dom_ms, "kernel_share_of_step": filter_share,
                 "all_kernels_ms_per_step": k_ms,
                 "note": "the search is integer-issue bound, not HBM bound (SURVEY.md F8); see issue and profiles/"}
         line = {

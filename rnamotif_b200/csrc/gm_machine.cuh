@@ -124,7 +124,7 @@ struct PairBits {
 // starts at window position z can have its first `req` pairs formed with at
 // most `budget` mispairs -- a superset of the span ends match_wchlx accepts.
 // bit j of the result <-> s3 = lo + j.
-__device__ __noinline__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
+__device__ __forceinline__ uint64_t wc_mask_body(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
 	int dupi, int flt, int z, int lo, int n)
 {
 	const uint64_t ones = n >= 64 ? ~0ull : ((1ull << n) - 1);
@@ -162,6 +162,15 @@ __device__ __noinline__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, 
 		}
 	}
 	return (budget == 0 ? a0 : budget == 1 ? a1 : a2) & ones;
+}
+
+// Out of line for the lite machine and the filters (their hot loops have to stay
+// small: the kernels are instruction-cache sensitive); the full machine, whose
+// pseudoknot loops call it per 3' end, inlines the body.
+__device__ __noinline__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
+	int dupi, int flt, int z, int lo, int n)
+{
+	return wc_mask_body(pb, sq, strand, sqbase, dupi, flt, z, lo, n);
 }
 
 // The level-0 sieve: the span-end test of wc_mask for 32 consecutive helix
@@ -971,7 +980,9 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					break;
 			}
 
-#define GM_MASK(S, z, clo, n) wc_mask(mypb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n))
+#define GM_MASK(S, z, clo, n)                                                                          \
+	(FULL ? wc_mask_body(mypb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n))               \
+	      : wc_mask(mypb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n)))
 #define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, strand, sqbase, (S), (T), (s5), (s3), (hl))
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
