@@ -160,6 +160,21 @@ static search_kernel_t pre_kernel(int pf)
 
 #define GM_WL_SEG_NT ((int64_t)16 << 20) // default segment of the split path, nucleotides
 
+// Worklist capacity in entries: every start of a default segment, both strands.
+// GPUMOTIF_WL_CAP shrinks it (tests of the overflow path).
+static size_t wl_entries()
+{
+	const char *e = getenv("GPUMOTIF_WL_CAP");
+	if (e != NULL && atoll(e) >= 1024)
+		return (size_t)atoll(e);
+	return (size_t)GM_WL_SEG_NT * 2;
+}
+// the segment that can never overflow the worklist
+static int64_t wl_safe_seg()
+{
+	return (int64_t)(wl_entries() / 2);
+}
+
 static int kind_of(const gm_plan_t *pl, int d)
 {
 	const gm_elem_t &e = pl->elems[d];
@@ -747,7 +762,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->dev_sorted = false;
 	c->hits_view = NULL;
 	c->n_seg_ev = 0;
-	c->seg_nt = GM_WL_SEG_NT;
+	c->seg_nt = getenv("GPUMOTIF_SEG_NT") != NULL && atoll(getenv("GPUMOTIF_SEG_NT")) > 0 ? atoll(getenv("GPUMOTIF_SEG_NT")) : wl_safe_seg();
 	c->use_split = false;
 	c->chars_cap = c->packed_cap = c->rec_cap = 0;
 	c->total_nt = 0;
@@ -1205,7 +1220,7 @@ static int launch(gm_ctx *c)
 		// tail -- a handful of long enumerations -- is paid once per segment); if a
 		// segment then overflows after all, the scan is repeated with default
 		// segments (gm_scan_finish), nothing is lost.
-		const size_t need = (size_t)GM_WL_SEG_NT * 2;
+		const size_t need = wl_entries();
 		const int64_t seg = std::min<int64_t>(c->seg_nt, c->p_end - c->p_begin);
 		if (c->d_wl == NULL || c->wl_cap < need) {
 			cudaFree(c->d_wl);
@@ -1343,9 +1358,9 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 				cnt[1], cnt[2], cnt[3], cnt[5]);
 		if (c->use_split && cnt[7]) {
 			// a grown segment overflowed the worklist: repeat with default segments
-			if (c->seg_nt <= GM_WL_SEG_NT)
+			if (c->seg_nt <= wl_safe_seg())
 				return fail("worklist overflow with default segments (internal error)");
-			c->seg_nt = GM_WL_SEG_NT;
+			c->seg_nt = wl_safe_seg();
 			c->stats.n_retries++;
 			if (launch(c))
 				return -1;
@@ -1355,10 +1370,10 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 			// survivors per start of this scan -> segment size of the next one, so that
 			// a segment fills at most a quarter of the worklist
 			const double rate = (double)cnt[6] / ((double)(c->p_end - c->p_begin) * c->p_strands);
-			const double cap = (double)GM_WL_SEG_NT * 2;
+			const double cap = (double)wl_entries();
 			double seg = rate > 0 ? 0.25 * cap / (rate * c->p_strands) : 1e18;
-			seg = std::max<double>((double)GM_WL_SEG_NT, std::min<double>(seg, (double)((int64_t)1 << 30)));
-			c->seg_nt = (int64_t)seg / GM_WL_SEG_NT * GM_WL_SEG_NT;
+			seg = std::max<double>((double)wl_safe_seg(), std::min<double>(seg, (double)((int64_t)1 << 30)));
+			c->seg_nt = (int64_t)seg / wl_safe_seg() * wl_safe_seg();
 		}
 		if (cnt[1] <= c->hit_cap)
 			break;

@@ -95,3 +95,43 @@ def test_empty_and_tiny_inputs():
     assert len(ms.find_motif(np.zeros(0, np.uint8), np.array([0], np.int64))) == 0
     assert len(ms.find_motif(np.frombuffer(b"acgu", np.uint8), np.array([0, 0, 4, 4], np.int64))) == 0
     ms.close()
+
+
+@pytest.mark.parametrize("path", ["fused", "split"])
+@pytest.mark.parametrize("name", ["trna", "descr.trna.general", "score.1", "pk1", "qu+tr", "ire", "mp.ends.strict"])
+def test_both_paths_match_oracle(name, path, monkeypatch):
+    """The fused kernel and the worklist pair (filter kernel -> enumeration kernel)
+    must both give the oracle's candidate stream, whichever the library would pick
+    for the plan (GPUMOTIF_PATH is read when the context is configured)."""
+    monkeypatch.setenv("GPUMOTIF_PATH", path)
+    plan = helpers.load_plan(name)
+    rng = np.random.default_rng(77)
+    lengths = list(rng.integers(0, 2500, size=30)) + [120000, 1, 64]
+    ids, seq, off = synth.random_records(11, lengths, planted=True, iupac_rate=0.002)
+    both = bool(gpumotif.plan_field(plan, 8))
+    ref, _ = oracle_port.scan_db(plan, seq, off, both)
+    ms = gpumotif.MotifSearch(plan)
+    hits = ms.find_motif(seq, off)
+    ms.close()
+    helpers.assert_same_hits(hits, ref, f"{name} ({path})")
+
+
+def test_worklist_overflow_is_recovered(monkeypatch):
+    """Segments of the worklist path grow with the measured survivor rate; one that
+    overflows the worklist after all is detected and the scan repeated with segments
+    that cannot (gm_scan_finish).  Forced here with a tiny worklist."""
+    monkeypatch.setenv("GPUMOTIF_PATH", "split")
+    monkeypatch.setenv("GPUMOTIF_WL_CAP", "2048")
+    monkeypatch.setenv("GPUMOTIF_SEG_NT", "4000000")
+    plan = helpers.load_plan("score.1")
+    ids, seq, off = synth.random_records(5, [150000, 3000, 90000], planted=True)
+    both = bool(gpumotif.plan_field(plan, 8))
+    ref, _ = oracle_port.scan_db(plan, seq, off, both)
+    ms = gpumotif.MotifSearch(plan)
+    hits = ms.find_motif(seq, off)
+    retries = ms.stats().n_retries
+    again = ms.find_motif(seq, off)  # second scan: segment size settled
+    ms.close()
+    assert retries >= 1, "the tiny worklist should have overflowed on the first scan"
+    helpers.assert_same_hits(hits, ref, "after worklist overflow")
+    helpers.assert_same_hits(again, ref, "scan after the overflow")
