@@ -984,10 +984,13 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	(FULL ? wc_mask_body(mypb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n))               \
 	      : wc_mask(mypb, L.sq, strand, sqbase, (S).dupi, (S).flt, (z), (clo), (n)))
 #define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, strand, sqbase, (S), (T), (s5), (s3), (hl))
+// 64 bits of the base bitset of base x (table 0) from window-relative position p on
+#define GM_BBITS(x, p) bits64(mypb.base + ((size_t)(strand * mypb.n_dups) * 4 + (x)) * mypb.nwb, sqbase + (p))
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
 #undef GM_TAIL
+#undef GM_BBITS
 #undef GM_MASK
 		}
 	}
@@ -1178,10 +1181,12 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 			break;
 #define GM_MASK(S, z, clo, n) wc_mask(mypb, L.sq, 0, Lc, (S).dupi, (S).flt, (z), (clo), (n))
 #define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, 0, Lc, (S), (T), (s5), (s3), (hl))
+#define GM_BBITS(x, p) bits64(mypb.base + (size_t)(x) * mypb.nwb, Lc + (p))
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
 #undef GM_TAIL
+#undef GM_BBITS
 #undef GM_MASK
 	}
 }
