@@ -327,8 +327,9 @@ __device__ __forceinline__ bool tail_feasible(const PairBits &pb, const uint8_t 
 template <int MODE, bool FULL, int PF>
 __global__ void gm_search_kernel(const ScanArgs A)
 {
-	constexpr bool LIT = PF == 1;   // literal prefilter
 	constexpr bool SIEVE = PF == 2; // word-parallel level-0 sieve instead of the per-start prefilter
+	// literal prefilter: per start (PF == 1) or as one more term of the sieve
+	const bool LIT = PF == 1 || (SIEVE && c_par.lit_present != 0);
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, nt = blockDim.x;
 	const int lane = tid & 31, warp = tid >> 5;
@@ -526,29 +527,32 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		}
 		if (LIT) {
 			// literal prefilter (adjust_szero, src/find_motif.c:209-243): bit i of a
-			// strand's set = the best literal occurs at tile position i within its
-			// mismatch allowance (mm_advance on fixed-length items, src/mm_regexp.c:369-469)
+			// strand's set = the best literal can occur at tile position i within its
+			// mismatch allowance (mm_advance on fixed-length items, src/mm_regexp.c:369-469).
+			// Word arithmetic over the base bitsets, one word per lane: pattern position
+			// k accepts base x if its class mask says so, and any nucleotide that is not
+			// plain a/c/g/t counts as accepted -- a superset of the true occurrences
+			// (survivors take the exact tests in the machine).
 			const int len = c_par.lit_len, l_mm = c_par.lit_mm;
 			const uint64_t dot = c_plan.regex[c_par.lit_rx].dot;
-			for (int w = 0; w < nwb; w++) {
-				const int i = w * 32 + lane;
-				bool mf = i + len <= Lbytes, mr = mf;
-				int cf = 0, cr = 0;
-				for (int k = 0; k < len && (mf || mr); k++) {
-					const uint64_t bit = (uint64_t)1 << k;
-					if (dot & bit)
+			const uint64_t sel0 = sm_litB[1], sel1 = sm_litB[2], sel2 = sm_litB[4], sel3 = sm_litB[8];
+			for (int idx = lane; idx < 2 * nwb; idx += 32) {
+				const int st = idx >= nwb, w = idx - st * nwb;
+				const uint32_t *Bs = pbw + (size_t)(st * n_dups) * 4 * nwb;
+				uint32_t a0 = ~0u, a1 = ~0u, a2 = ~0u;
+				for (int k = 0; k < len; k++) {
+					if ((dot >> k) & 1)
 						continue;
-					if (mf && !(sm_litB[icode_of(sm_fwd[i + k])] & bit) && ++cf > l_mm)
-						mf = false;
-					if (mr && !(sm_litB[icode_of(sm_rc[i + k])] & bit) && ++cr > l_mm)
-						mr = false;
+					const int q = min((w << 5) + k, Lbytes);
+					const uint32_t b0 = bits32(Bs, q), b1 = bits32(Bs + nwb, q), b2 = bits32(Bs + 2 * nwb, q),
+						b3 = bits32(Bs + 3 * nwb, q);
+					const uint32_t m = ~(b0 | b1 | b2 | b3) | (((sel0 >> k) & 1) ? b0 : 0u) | (((sel1 >> k) & 1) ? b1 : 0u) |
+						(((sel2 >> k) & 1) ? b2 : 0u) | (((sel3 >> k) & 1) ? b3 : 0u);
+					a2 = (a2 & m) | a1;
+					a1 = (a1 & m) | a0;
+					a0 &= m;
 				}
-				const unsigned bf = __ballot_sync(0xffffffffu, mf);
-				const unsigned br = __ballot_sync(0xffffffffu, mr);
-				if (lane == 0) {
-					sm_lit[w] = bf;
-					sm_lit[nwb + w] = br;
-				}
+				sm_lit[idx] = l_mm == 0 ? a0 : l_mm == 1 ? a1 : l_mm == 2 ? a2 : ~0u;
 			}
 		}
 		__syncwarp();
@@ -759,7 +763,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	};
 	// the lane's word of pass `pass` over the tile's helix starts (strand-major)
 	auto sieve_pass = [&](int pass, int &strand_, int &w_) -> uint32_t {
-		const DevSearch &SP = sm_ds[c_par.pf_search];
+		const DevSearch &SP = sm_ds[max(c_par.pf_search, 0)]; // (unused by a literal-only sieve)
 		const int pz = c_par.pf_z;
 		const int nv = (int)(gB - gA); // starts of this tile
 		const int it = pass * 32 + lane;
@@ -782,7 +786,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				// ends asked about at span offset d: e0 + d + m, m = nhl-1-j for length minlen + j
 				const int e0 = (w_ << 5) - SP.minlen - SP.lk_off - (nhl - 1);
 				const bool has_lk = deep && SP.lk_t >= 0;
-				word = sieve_word(pb, strand_, SP.dupi, SP.flt, w_, SP.minglen - 1, SP.maxglen - 1,
+				word = !c_par.sv_helix ? ~0u : sieve_word(pb, strand_, SP.dupi, SP.flt, w_, SP.minglen - 1, SP.maxglen - 1,
 					[&](int d, uint32_t f) -> uint32_t {
 						if (!has_lk)
 							return f & (kh[0] | kh[1] | kh[2] | kh[3]);
@@ -796,6 +800,15 @@ __global__ void gm_search_kernel(const ScanArgs A)
 								la |= kh[j] & __funnelshift_r(lo_, hi_, nhl - 1 - j);
 						return f & la;
 					});
+				if (LIT) {
+					// literal prefilter as a sieve term: the best literal must begin
+					// lit_lmin..lit_lmax nucleotides after the start (= helix start - pz)
+					const uint32_t *set = sm_lit + strand_ * nwb;
+					uint32_t any = 0;
+					for (int l = c_par.lit_lmin; l <= c_par.lit_lmax; l++)
+						any |= bits32(set, min(max((w_ << 5) - pz + l, 0), Lbytes));
+					word &= any;
+				}
 				// keep the bits of this tile's own starts
 				const int b0 = w_ << 5;
 				if (zlo > b0)

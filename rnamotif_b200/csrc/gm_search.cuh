@@ -82,6 +82,7 @@ struct DevParams {
 	int pf_z;               // its 5' start relative to the window (fixed-length ss before it)
 	int sieve;              // level-0 sieve (sieve_word): word-parallel test of pf_search's span ends
 	int pf_deep;            // second stage behind the sieve: kid / tail look-ahead per span end
+	int sv_helix;           // the sieve has a helix term (pf_search); otherwise only the literal term
 	int sv_id;              // index in dups[] of the identity table (its bitsets are the base bitsets)
 	int lit_present;        // literal prefilter (gm_plan_t::literal): regex index, window, length
 	int lit_rx, lit_lmin, lit_lmax, lit_mm, lit_len;

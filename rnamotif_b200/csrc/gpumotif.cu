@@ -487,12 +487,14 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	// bitsets = pair bitsets of the identity table, and a budget of at most one)
 	par->sieve = 0;
 	par->sv_id = -1;
-	if (par->pf_search >= 0 && !par->lit_present && getenv("GPUMOTIF_NO_SIEVE") == NULL) {
+	par->sv_helix = 0;
+	if (par->pf_search >= 0 && getenv("GPUMOTIF_NO_SIEVE") == NULL) {
 		const DevSearch &SP = ds[par->pf_search];
 		const int req = SP.flt & 0xff, budget = (SP.flt >> 8) & 0xff;
 		if ((SP.kind == K_WC || SP.kind == K_QU) && req >= 1 && budget <= 1 &&
 		    SP.minglen - 1 - 2 * (req - 1) >= 1 && SP.maxglen - SP.minglen <= 160) {
 			par->sieve = 1;
+			par->sv_helix = 1;
 			par->sv_id = 0;
 			// look-ahead inside the sieve when the first helix has targets (themselves
 			// sievable: a budget of at most one) and few lengths to try
@@ -510,6 +512,9 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 				par->pf_deep = 2;
 		}
 	}
+	// a literal alone also makes a sieve (its occurrence bitset, ORed over the window)
+	if (!par->sieve && par->lit_present && par->lit_lmax - par->lit_lmin <= 256 && getenv("GPUMOTIF_NO_SIEVE") == NULL)
+		par->sieve = 1;
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
 		if ((ds[s].kind != K_SS && ds[s].kind != K_WC) || ds[s].hmm)
