@@ -135,3 +135,21 @@ def test_worklist_overflow_is_recovered(monkeypatch):
     assert retries >= 1, "the tiny worklist should have overflowed on the first scan"
     helpers.assert_same_hits(hits, ref, "after worklist overflow")
     helpers.assert_same_hits(again, ref, "scan after the overflow")
+
+
+@pytest.mark.parametrize("knob", ["GPUMOTIF_NO_SIEVE", "GPUMOTIF_NO_DEEP", "GPUMOTIF_NO_DEEP2", "GPUMOTIF_NO_TAIL",
+                                  "GPUMOTIF_NO_LITERAL", "GPUMOTIF_HOST_SORT"])
+@pytest.mark.parametrize("name", ["trna", "ire", "pk1"])
+def test_filters_are_output_neutral(name, knob, monkeypatch):
+    """Every level-0 filter and look-ahead only prunes what cannot reach the hit
+    sink, and the device-side ordering equals the host's: with any of them switched
+    off the candidate stream is still the oracle's."""
+    monkeypatch.setenv(knob, "1")
+    plan = helpers.load_plan(name)
+    ids, seq, off = synth.random_records(23, [40000, 700, 0, 9000, 65000], planted=True, iupac_rate=0.003)
+    both = bool(gpumotif.plan_field(plan, 8))
+    ref, _ = oracle_port.scan_db(plan, seq, off, both)
+    ms = gpumotif.MotifSearch(plan)
+    hits = ms.find_motif(seq, off)
+    ms.close()
+    helpers.assert_same_hits(hits, ref, f"{name} with {knob}")
