@@ -187,10 +187,12 @@ __device__ __noinline__ uint64_t wc_mask(const PairBits &pb, const uint8_t *sq, 
 // superset of it when it is.
 // `fin(d, f)` sees every completed span offset d >= Dlo with its word f and
 // returns what of it counts (the identity, a look-ahead filter, ...).
-template <typename Fin>
-__device__ __forceinline__ uint32_t sieve_word(const PairBits &pb, int strand, int dupi, int flt, int w, int Dlo, int Dhi, Fin fin)
+template <int REQ, typename Fin>
+__device__ __forceinline__ uint32_t sieve_word_r(const PairBits &pb, int strand, int dupi, int flt, int w, int Dlo, int Dhi, Fin fin)
 {
-	const int req = flt & 0xff, budget = (flt >> 8) & 0xff, first_must = (flt >> 16) & 1;
+	constexpr int NS_ = REQ > 0 ? REQ : 8; // accumulator slots
+	const int req = REQ > 0 ? REQ : (flt & 0xff);
+	const int budget = (flt >> 8) & 0xff, first_must = (flt >> 16) & 1;
 	const int nwb = pb.nwb;
 	const uint32_t *P = pb.base + ((size_t)(strand * pb.n_dups + dupi) * 4) * nwb;
 	const uint32_t *I = pb.base + ((size_t)(strand * pb.n_dups) * 4) * nwb; // table 0: base bitsets
@@ -206,9 +208,9 @@ __device__ __forceinline__ uint32_t sieve_word(const PairBits &pb, int strand, i
 		// a0[k] / a1[k]: products (no mispair / at most one) of the span offset that
 		// is k steps from completion; the loop is kept rolled (rotating the
 		// registers) so that it stays inside the L0 instruction cache
-		uint32_t a0[8], a1[8];
+		uint32_t a0[NS_], a1[NS_];
 #pragma unroll
-		for (int u = 0; u < 8; u++)
+		for (int u = 0; u < NS_; u++)
 			a0[u] = a1[u] = ~0u;
 		for (int d = Dmin + par; d <= Dhi; d += 2) {
 			const int ww = min(w + (d >> 5), nwb - 3), sh = d & 31;
@@ -220,8 +222,8 @@ __device__ __forceinline__ uint32_t sieve_word(const PairBits &pb, int strand, i
 				Mh |= Bh[x] & __funnelshift_r(c1, c2, sh);
 			}
 #pragma unroll
-			for (int k = 7; k >= 1; k--) {
-				if (k < req) {
+			for (int k = NS_ - 1; k >= 1; k--) {
+				if (REQ > 0 || k < req) {
 					const uint32_t t = __funnelshift_r(Ml, Mh, k);
 					a1[k] = (a1[k] & t) | a0[k];
 					a0[k] &= t;
@@ -238,14 +240,34 @@ __device__ __forceinline__ uint32_t sieve_word(const PairBits &pb, int strand, i
 			if (d >= Dlo)
 				res |= fin(d, f);
 #pragma unroll
-			for (int u = 0; u < 7; u++) {
+			for (int u = 0; u < NS_ - 1; u++) {
 				a0[u] = a0[u + 1];
 				a1[u] = a1[u + 1];
 			}
-			a0[7] = a1[7] = ~0u;
+			a0[NS_ - 1] = a1[NS_ - 1] = ~0u;
 		}
 	}
 	return res;
+}
+
+template <typename Fin>
+__device__ __forceinline__ uint32_t sieve_word(const PairBits &pb, int strand, int dupi, int flt, int w, int Dlo, int Dhi, Fin fin)
+{
+	return sieve_word_r<0>(pb, strand, dupi, flt, w, Dlo, Dhi, fin);
+}
+// the main pass: the number of required pairs as a compile-time constant (no
+// predicates, no dead accumulator slots in the hot loop)
+template <typename Fin>
+__device__ __forceinline__ uint32_t sieve_word_main(const PairBits &pb, int strand, int dupi, int flt, int w, int Dlo, int Dhi, Fin fin)
+{
+	switch (flt & 0xff) {
+	case 3: return sieve_word_r<3>(pb, strand, dupi, flt, w, Dlo, Dhi, fin);
+	case 4: return sieve_word_r<4>(pb, strand, dupi, flt, w, Dlo, Dhi, fin);
+	case 5: return sieve_word_r<5>(pb, strand, dupi, flt, w, Dlo, Dhi, fin);
+	case 6: return sieve_word_r<6>(pb, strand, dupi, flt, w, Dlo, Dhi, fin);
+	case 7: return sieve_word_r<7>(pb, strand, dupi, flt, w, Dlo, Dhi, fin);
+	}
+	return sieve_word_r<0>(pb, strand, dupi, flt, w, Dlo, Dhi, fin);
 }
 
 // 32 bits of a bitset from bit q on (q >= 0)
@@ -786,7 +808,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				// ends asked about at span offset d: e0 + d + m, m = nhl-1-j for length minlen + j
 				const int e0 = (w_ << 5) - SP.minlen - SP.lk_off - (nhl - 1);
 				const bool has_lk = deep && SP.lk_t >= 0;
-				word = !c_par.sv_helix ? ~0u : sieve_word(pb, strand_, SP.dupi, SP.flt, w_, SP.minglen - 1, SP.maxglen - 1,
+				word = !c_par.sv_helix ? ~0u : sieve_word_main(pb, strand_, SP.dupi, SP.flt, w_, SP.minglen - 1, SP.maxglen - 1,
 					[&](int d, uint32_t f) -> uint32_t {
 						if (!has_lk)
 							return f & (kh[0] | kh[1] | kh[2] | kh[3]);
