@@ -1,23 +1,30 @@
-// gm_machine.cuh -- gm_search_kernel: tile staging, span-end prefilter, and
-// the search machine.
+// gm_machine.cuh -- the search kernels: tile staging, level-0 filters, and the
+// search machine.
 //
-// Per tile (TILE consecutive nucleotides of the concatenated database, both
-// strands):
-//   1. one TMA bulk copy brings the packed tile + halo into shared memory;
-//      it is expanded to one byte per nucleotide for the forward strand and
-//      for the reverse complement (mk_rcmp, src/rnamot.c:193-216);
-//   2. "pair bitsets" are built with __ballot_sync: for every distinct duplex
-//      table D used by a helix head and every base x, bit p of P[D][x] says
-//      whether x pairs with the nucleotide at tile position p.  With them the
-//      set of span ends whose outermost `req` pairs can form is a handful of
-//      funnel shifts and ANDs (wc_mask) instead of a loop over span ends;
-//   3. warps pull chunks of 32 start positions; a start whose level-0 mask is
-//      empty (or whose anchored seq= cannot match) is dropped at once, the
-//      others go to a small per-warp queue;
-//   4. lanes take starts from the queue and run the explicit-stack machine.
-//      The masks are hints that only ever remove span ends match_wchlx would
-//      reject at its first tests (src/find_motif.c:1010-1079); every survivor
-//      goes through the full test, so the enumeration is unchanged.
+// gm_search_kernel<MODE, FULL, PF>, per tile (TILE consecutive nucleotides of
+// the concatenated database, both strands):
+//   1. one TMA bulk copy brings the packed tile + halo into shared memory; it is
+//      expanded to one byte per nucleotide for the forward strand and for the
+//      reverse complement (mk_rcmp, src/rnamot.c:193-216);
+//   2. base bitsets (bit p of set x: base(p) == x) come from four ballots per 32
+//      nucleotides; the reverse-complement strand's are their bit-reversed words,
+//      and the "pair bitsets" of every distinct duplex table D (bit p of P[D][x]:
+//      x pairs with the nucleotide at p) are unions of them, one word per lane;
+//   3. the level-0 filter drops the starts that cannot begin a match:
+//        PF 2  the sieve (sieve_word): the span-end test of the first helix for
+//              32 starts per lane as word operations, with look-ahead bitsets for
+//              the first / last helix of its interior and the literal prefilter
+//              as further terms;
+//        PF 0  per start: the 64-bit candidate mask of the first helix (wc_mask);
+//        PF 1  the same plus the literal prefilter per start;
+//   4. MODE 0 (fused): survivors go to a per-warp queue, lanes take them and run
+//      the explicit-stack machine (gm_machine_body.inc) on the tile in shared
+//      memory; MODE 1: survivors are appended to a global worklist that
+//      gm_dfs_kernel consumes with per-lane windows (the worklist path, the
+//      default where the filter is strong -- see DESIGN.md section 4).
+// Every filter and mask only removes what match_wchlx would reject at its first
+// tests (src/find_motif.c:1010-1079) or subtrees that cannot reach the hit sink;
+// every survivor goes through the full test, so the enumeration is unchanged.
 #pragma once
 
 #include "gm_kernel.cuh"
@@ -1040,30 +1047,11 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		atomicAdd(A.start_count + 3, (unsigned long long)my_entries);
 }
 
-// First-pair scan used where no pair bitsets exist (gm_dfs_kernel): span ends
-// in [lo, lo+n) whose outermost pair can form -- what match_wchlx tests first
-// (src/find_motif.c:1010-1021).  A superset filter like wc_mask.
-__device__ __forceinline__ uint64_t wc_mask_scan(const Lane &L, const DevSearch &S, int z, int lo, int n)
-{
-	const uint64_t ones = n >= 64 ? ~0ull : ((1ull << n) - 1);
-	if (!((S.flt >> 16) & 1) || S.minlen == 0)
-		return ones;
-	const unsigned row = S.duplex >> (bcode_of(L.sq[z]) * 5);
-	uint64_t v = 0;
-	for (int j = 0; j < n; j++)
-		v |= (uint64_t)((row >> bcode_of(L.sq[lo + j])) & 1u) << j;
-	return v;
-}
-
-struct DfsSmem {
-	int dummy[16];
-};
-
-// The worklist consumer of the split path: lanes take prefilter survivors from
-// the global worklist (32 at a time per warp), the warp cooperatively builds
-// each new lane's private window (one byte per nucleotide of the searched
-// strand, reverse complement included) straight from the packed database, and
-// the lanes run the same machine as the tile kernel.
+// The enumeration kernel of the worklist path: idle lanes take the filter's
+// survivors from the global worklist in batches; every lane builds its own
+// window (one byte per nucleotide of the searched strand, reverse complement
+// included) and its own pair bitsets straight from the packed database, and the
+// lanes run the same machine, with the same masks, as the tile kernel.
 template <bool FULL>
 __global__ void gm_dfs_kernel(const ScanArgs A)
 {
