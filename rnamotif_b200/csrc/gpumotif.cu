@@ -1235,6 +1235,12 @@ static int launch(gm_ctx *c)
 		}
 		A.wl = c->d_wl;
 		A.wl_cap = c->wl_cap;
+		// When the whole range fits one segment (few survivors) but arrives in
+		// chunks, the filter kernel runs per chunk and appends to ONE worklist; the
+		// enumeration kernel runs once at the end (its latency tail is paid once).
+		const bool defer_dfs = stream_in && seg >= c->p_end - c->p_begin;
+		if (defer_dfs)
+			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
 		int ci = 0;
 		for (int64_t g0 = c->p_begin; g0 < c->p_end; g0 = A.g_end) {
 			A.g_begin = g0;
@@ -1250,7 +1256,8 @@ static int launch(gm_ctx *c)
 			A.n_tiles = (A.g_end - A.g_begin + c->par.tile - 1) / c->par.tile;
 			// tile counter, worklist count and head restart for every segment
 			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
-			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
+			if (!defer_dfs)
+				CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
 			int ablocks = (int)std::min<int64_t>(c->a_blocks, A.n_tiles);
 			while ((int)c->seg_ev.size() < 2 * (c->n_seg_ev + 1)) {
 				cudaEvent_t e;
@@ -1262,9 +1269,17 @@ static int launch(gm_ctx *c)
 			CU(cudaGetLastError());
 			CU(cudaEventRecord(c->seg_ev[2 * c->n_seg_ev + 1], c->stream));
 			c->n_seg_ev++;
+			c->stats.n_launches++;
+			if (!defer_dfs) {
+				dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
+				CU(cudaGetLastError());
+				c->stats.n_launches++;
+			}
+		}
+		if (defer_dfs) {
 			dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
-			c->stats.n_launches += 2;
+			c->stats.n_launches++;
 		}
 	}
 	CU(cudaEventRecord(c->ev[4], c->stream));

@@ -153,3 +153,19 @@ def test_filters_are_output_neutral(name, knob, monkeypatch):
     hits = ms.find_motif(seq, off)
     ms.close()
     helpers.assert_same_hits(hits, ref, f"{name} with {knob}")
+
+
+@pytest.mark.parametrize("name", ["trna", "score.1", "pk_j1+2", "ire"])
+def test_start_count_matches_oracle(name):
+    """gm_scan_stats_t::n_starts = (start, strand) pairs RM_find_motif would search
+    (szero in [0, slen - rm_dminlen], src/find_motif.c:184-205): counted by the kernel
+    where it visits starts one by one, by the host where the sieve does not."""
+    plan = helpers.load_plan(name)
+    ids, seq, off = synth.random_records(31, [5000, 0, 12, 62, 63, 64, 100, 30000, 7], planted=False)
+    both = bool(gpumotif.plan_field(plan, 8))
+    _, ost = oracle_port.scan_db(plan, seq, off, both)
+    ms = gpumotif.MotifSearch(plan)
+    ms.find_motif(seq, off)
+    n = ms.stats().n_starts
+    ms.close()
+    assert n == ost.n_starts, f"{name}: {n} starts vs oracle {ost.n_starts}"
