@@ -851,6 +851,8 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 		cudaStreamSynchronize(c->copy_stream);
 	for (cudaEvent_t e : c->chunk_ev)
 		cudaEventDestroy(e);
+	for (cudaEvent_t e : c->seg_ev)
+		cudaEventDestroy(e);
 	for (int i = 0; i < 2; i++)
 		if (c->up_ev[i])
 			cudaEventDestroy(c->up_ev[i]);
