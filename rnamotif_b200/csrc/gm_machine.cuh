@@ -749,7 +749,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const int hi_ = min(zhi + SP.maxglen - 1 - SP.minlen - SP.lk_off - (T.minglen - 1), Lbytes - 1);
 				uint32_t *E = sv_E + st * nwb;
 				for (int w = (lo_ >> 5) + lane; w <= (hi_ >> 5) && w < nw; w += 32)
-					sieve_word(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
+					sieve_word_main(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
 						[&](int d, uint32_t f) -> uint32_t {
 							// the helix that starts at bit t ends at t + d
 							const int q = (w << 5) + d, sh = q & 31;
@@ -775,13 +775,13 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					const int lo2 = (lo_ & ~31) + T.minglen + T.sib_off;
 					const int hi2 = min((hi_ | 31) + T.maxglen + T.sib_off + 31, Lbytes - 1);
 					for (int w = (lo2 >> 5) + lane; w <= (hi2 >> 5) && w < nw; w += 32)
-						sv_K2[st * nwb + w] = sieve_word(pb, st, T2.dupi, T2.flt, w, T2.minglen - 1, T2.maxglen - 1,
+						sv_K2[st * nwb + w] = sieve_word_main(pb, st, T2.dupi, T2.flt, w, T2.minglen - 1, T2.maxglen - 1,
 							[](int, uint32_t f) -> uint32_t { return f; });
 					__syncwarp();
 				}
 				const int k2off = T.sib_off + 1;
 				for (int w = (lo_ >> 5) + lane; w <= (hi_ >> 5) && w < nw; w += 32)
-					sv_K[st * nwb + w] = sieve_word(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
+					sv_K[st * nwb + w] = sieve_word_main(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
 						[&](int d, uint32_t f) -> uint32_t {
 							// span offset d: the group ends at start + d, its sibling begins k2off later
 							return has_k2 ? f & bits32(K2, min((w << 5) + d + k2off, Lbytes)) : f;
