@@ -152,6 +152,26 @@ int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, size_t *str
 
 int gm_stats(const gm_ctx *c, gm_scan_stats_t *out);
 
+/*
+ * rmprune over the binary candidate stream.  The reference's
+ * rmprune (src/rmprune.c:332-617) reads rnamotif's text output and drops the
+ * hits that are "unzipped" versions of another hit of the same locus and
+ * strand: same helices, one of them merely shorter at its outer or inner end
+ * (wchlxrel, :700-741).  This is the same decision taken on gm_hits() records,
+ * which carry everything rmprune reconstructs from the text (strand, start,
+ * element lengths): keep[i] = 1 if hit i stays, 0 if rmprune would drop it.
+ * `hits`, `n`, `stride` as returned by gm_hits() (enumeration order = the order
+ * of rnamotif's output); `group[i]` tells which hits form a block (rmprune
+ * groups consecutive hits by locus name, :172-186) -- NULL groups by record.
+ * Reference behaviour kept: blocks are cut after 1000 hits (:82,183-186), a
+ * zero-length element counts one column (print_match writes "."), the
+ * forward hits of a block are expected before its complementary ones.  Context
+ * columns (-context) are not part of a hit record and are ignored.  Host
+ * code only: needs no device.
+ */
+int gm_prune_hits(const gm_plan_t *plan, const void *hits, size_t n, size_t stride,
+                  const int32_t *group, uint8_t *keep);
+
 /* Tunables (before the first scan): hit-buffer capacity in records (default
  * 1<<20; grown automatically when a scan overflows), starts per tile. */
 int gm_set_hit_capacity(gm_ctx *c, size_t n_records);

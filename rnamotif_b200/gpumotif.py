@@ -71,8 +71,23 @@ def lib():
         L.gm_set_tile.argtypes = [C.c_void_p, C.c_int]
         L.gm_stream.argtypes = [C.c_void_p]
         L.gm_stream.restype = C.c_void_p
+        L.gm_prune_hits.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def prune_hits(plan: bytes, hits: np.ndarray, group=None) -> np.ndarray:
+    """rmprune (src/rmprune.c) over a candidate array in enumeration order:
+    boolean mask of the hits rmprune keeps.  `group[i]` = block (locus) of hit i,
+    default: its record.  Host code, needs no device."""
+    hits = np.ascontiguousarray(hits)
+    keep = np.ones(len(hits), dtype=np.uint8)
+    g = None if group is None else np.ascontiguousarray(group, dtype=np.int32)
+    rc = lib().gm_prune_hits(plan, hits.ctypes.data if len(hits) else None, len(hits), hits.dtype.itemsize,
+                             None if g is None else g.ctypes.data, keep.ctypes.data)
+    if rc != 0:
+        raise GpuMotifError("gm_prune_hits: " + _err())
+    return keep.astype(bool)
 
 
 def _err():
