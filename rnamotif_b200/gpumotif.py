@@ -38,7 +38,7 @@ EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_ctx_create", "g
            "gm_plan_check", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
            "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
-           "gm_set_hit_capacity", "gm_set_tile", "gm_stream"]
+           "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits"]
 
 
 def lib():
