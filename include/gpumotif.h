@@ -172,6 +172,24 @@ int gm_stats(const gm_ctx *c, gm_scan_stats_t *out);
 int gm_prune_hits(const gm_plan_t *plan, const void *hits, size_t n, size_t stride,
                   const int32_t *group, uint8_t *keep);
 
+/*
+ * rmfmt's ordering over hit records.  rmfmt sorts rnamotif's
+ * hit lines with sort(1) (src/rmfmt.c:240-262): scored output by
+ * `-k 2rn,2 -k 1,1 -k 3n,3 -k 4n,4 -k 5n,5` = score descending, then name,
+ * strand, printed position, total length; unscored output by name, strand,
+ * position, length.  perm[k] = index of the hit that comes k-th.
+ *   score      one value per hit (what RM_score left in rm_sval), or NULL
+ *   name_rank  per hit: rank of its (formatted) locus name in the byte order
+ *              sort(1) uses in the C locale; equal names share a rank
+ *   rec_off    record table of the database (n_rec + 1 entries): the printed
+ *              position on the complementary strand counts from the record's
+ *              end (print_match, src/find_motif.c:1842-1846)
+ * Hits equal in all keys keep their input (enumeration) order; sort(1) would
+ * compare the whole lines there.  Host code only.
+ */
+int gm_order_hits(const void *hits, size_t n, size_t stride, int n_descr, const double *score,
+                  const int32_t *name_rank, const int64_t *rec_off, int n_rec, uint32_t *perm);
+
 /* Tunables (before the first scan): hit-buffer capacity in records (default
  * 1<<20; grown automatically when a scan overflows), starts per tile. */
 int gm_set_hit_capacity(gm_ctx *c, size_t n_records);

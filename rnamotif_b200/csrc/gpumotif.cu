@@ -1794,6 +1794,49 @@ extern "C" int gm_prune_hits(const gm_plan_t *plan, const void *hits, size_t n, 
 	return 0;
 }
 
+extern "C" int gm_order_hits(const void *hits, size_t n, size_t stride, int n_descr, const double *score,
+	const int32_t *name_rank, const int64_t *rec_off, int n_rec, uint32_t *perm)
+{
+	if (perm == NULL || name_rank == NULL || rec_off == NULL || (n > 0 && hits == NULL) || n > 0xffffffffull)
+		return fail("bad argument");
+	if (n_descr < 1 || n_descr > GM_MAX_DESCR ||
+	    stride < sizeof(gm_hit_hdr_t) + (size_t)n_descr * sizeof(gm_hit_el_t))
+		return fail("hit stride %zu too small for %d elements", stride, n_descr);
+	const uint8_t *base = static_cast<const uint8_t *>(hits);
+	struct Key { double score; int32_t name; int32_t comp; int64_t pos; int32_t len; };
+	std::vector<Key> key(n);
+	for (size_t i = 0; i < n; i++) {
+		const gm_hit_hdr_t *h = reinterpret_cast<const gm_hit_hdr_t *>(base + i * stride);
+		const gm_hit_el_t *el = reinterpret_cast<const gm_hit_el_t *>(h + 1);
+		if ((int64_t)h->rec >= n_rec)
+			return fail("hit %zu: record %u outside the record table", i, h->rec);
+		Key &k = key[i];
+		k.score = score ? score[i] : 0.0;
+		k.name = name_rank[i];
+		k.comp = h->comp ? 1 : 0;
+		// print_match, src/find_motif.c:1838-1846
+		const int64_t slen = rec_off[h->rec + 1] - rec_off[h->rec];
+		k.pos = k.comp ? slen - el[0].off : (int64_t)el[0].off + 1;
+		k.len = 0;
+		for (int d = 0; d < n_descr; d++)
+			k.len += el[d].len;
+		perm[i] = (uint32_t)i;
+	}
+	std::stable_sort(perm, perm + n, [&](uint32_t a, uint32_t b) {
+		const Key &x = key[a], &y = key[b];
+		if (x.score != y.score)
+			return x.score > y.score; // -k 2rn
+		if (x.name != y.name)
+			return x.name < y.name;
+		if (x.comp != y.comp)
+			return x.comp < y.comp;
+		if (x.pos != y.pos)
+			return x.pos < y.pos;
+		return x.len < y.len;
+	});
+	return 0;
+}
+
 extern "C" int gm_stats(const gm_ctx *c, gm_scan_stats_t *out)
 {
 	if (c == NULL || out == NULL)

@@ -38,7 +38,7 @@ EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_ctx_create", "g
            "gm_plan_check", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
            "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
-           "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits"]
+           "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits", "gm_order_hits"]
 
 
 def lib():
@@ -72,6 +72,8 @@ def lib():
         L.gm_stream.argtypes = [C.c_void_p]
         L.gm_stream.restype = C.c_void_p
         L.gm_prune_hits.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.gm_order_hits.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -88,6 +90,24 @@ def prune_hits(plan: bytes, hits: np.ndarray, group=None) -> np.ndarray:
     if rc != 0:
         raise GpuMotifError("gm_prune_hits: " + _err())
     return keep.astype(bool)
+
+
+def order_hits(hits: np.ndarray, name_rank, rec_off, score=None) -> np.ndarray:
+    """rmfmt's ordering (src/rmfmt.c:240-262) over a candidate array: permutation
+    putting the hits in the order rmfmt prints them (score descending if given,
+    then name rank, strand, printed position, length).  Host code."""
+    hits = np.ascontiguousarray(hits)
+    nd = hits.dtype["el"].shape[0]
+    nr = np.ascontiguousarray(name_rank, dtype=np.int32)
+    ro = np.ascontiguousarray(rec_off, dtype=np.int64)
+    sc = None if score is None else np.ascontiguousarray(score, dtype=np.float64)
+    perm = np.zeros(len(hits), dtype=np.uint32)
+    rc = lib().gm_order_hits(hits.ctypes.data if len(hits) else None, len(hits), hits.dtype.itemsize, nd,
+                             None if sc is None else sc.ctypes.data, nr.ctypes.data, ro.ctypes.data, len(ro) - 1,
+                             perm.ctypes.data)
+    if rc != 0:
+        raise GpuMotifError("gm_order_hits: " + _err())
+    return perm
 
 
 def _err():
