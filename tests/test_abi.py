@@ -57,3 +57,13 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(gpumotif.GpuMotifError, match="no CUDA device"):
         gpumotif.MotifSearch(helpers.load_plan("trna"))
+
+
+def test_public_headers_are_plain_c():
+    """include/*.h is the drop-in boundary: C99, no C++ or torch types."""
+    import subprocess, tempfile
+    inc = os.path.join(helpers.ROOT, "include")
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "h.c")
+        open(src, "w").write('#include "gpumotif.h"\n#include "gpumotif_plan.h"\nint main(void){return 0;}\n')
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", src], check=True)
