@@ -1,0 +1,134 @@
+/*
+ * oracle/gm_mock.c -- TEST INFRASTRUCTURE.  A stand-in for the part of the C ABI
+ * of libgpumotif (include/gpumotif.h) that the reference-side host driver
+ * (rnamotif_b200/host/rm_gpu_main.c) calls, with the candidates coming from the
+ * plain-C oracle port (ref_search.c) instead of the device.  Linked ONLY into
+ * oracle/_ref/rnamotif_hostcheck, which tests/test_host_driver_cpu.py runs to
+ * check the HOST logic of the driver -- batching of records, sharding of a batch
+ * into start ranges and the ordered merge, the replay of the sink's tail through
+ * the reference's score program and printer -- byte for byte against the
+ * reference's stdout on a machine without a GPU.  Never part of the product:
+ * libgpumotif.so has no CPU search path.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gpumotif.h"
+
+typedef struct gmo_stats {
+	uint64_t n_starts, n_pair_evals, n_chk_seq, n_regex_steps, n_candidates;
+} gmo_stats_t;
+extern int64_t gmo_scan_db(const gm_plan_t *pl, const char *seq, const int64_t *rec_off, int n_rec, int both,
+	void *out, size_t out_cap, gmo_stats_t *stats);
+extern size_t gmo_hit_stride(const gm_plan_t *pl);
+
+struct gm_ctx {
+	gm_plan_t plan;
+	char *seq;
+	int64_t *off;
+	int n_rec;
+	int64_t lo, hi;
+	int strands;
+	char *hits;
+	size_t n, stride;
+};
+
+static char mock_err[256] = "";
+const char *gm_last_error(void) { return mock_err; }
+
+int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
+{
+	gm_ctx *c = calloc(1, sizeof *c);
+	(void)device;
+	if (c == NULL)
+		return -1;
+	c->plan = *plan;
+	c->stride = gmo_hit_stride(plan);
+	*out = c;
+	return 0;
+}
+
+void gm_ctx_destroy(gm_ctx *c)
+{
+	if (c == NULL)
+		return;
+	free(c->seq);
+	free(c->off);
+	free(c->hits);
+	free(c);
+}
+
+int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec)
+{
+	const int64_t total = rec_off[n_rec];
+	free(c->seq);
+	free(c->off);
+	c->seq = malloc((size_t)total + 1);
+	c->off = malloc((size_t)(n_rec + 1) * sizeof *c->off);
+	if (c->seq == NULL || c->off == NULL)
+		return -1;
+	memcpy(c->seq, seq, (size_t)total);
+	memcpy(c->off, rec_off, (size_t)(n_rec + 1) * sizeof *c->off);
+	c->n_rec = n_rec;
+	return 0;
+}
+
+int gm_scan_launch(gm_ctx *c, int64_t g_begin, int64_t g_end, int strands)
+{
+	c->lo = g_begin;
+	c->hi = g_end;
+	c->strands = strands;
+	return 0;
+}
+
+/* the oracle scans whole records; a context owns the starts whose 5' end (in the
+ * searched strand) falls on a nucleotide in [lo, hi), like gm_scan */
+int gm_scan_finish(gm_ctx *c)
+{
+	size_t cap = 1 << 16, i, k = 0;
+	int64_t n;
+	gmo_stats_t st;
+	for (;;) {
+		free(c->hits);
+		c->hits = malloc(cap * c->stride);
+		if (c->hits == NULL)
+			return -1;
+		memset(&st, 0, sizeof st);
+		n = gmo_scan_db(&c->plan, c->seq, c->off, c->n_rec, c->strands == 2, c->hits, cap * c->stride, &st);
+		if (n < 0) {
+			snprintf(mock_err, sizeof mock_err, "oracle scan failed");
+			return -1;
+		}
+		if ((size_t)n <= cap)
+			break;
+		cap = (size_t)n;
+	}
+	for (i = 0; i < (size_t)n; i++) {
+		const gm_hit_hdr_t *h = (const gm_hit_hdr_t *)(c->hits + i * c->stride);
+		const int64_t slen = c->off[h->rec + 1] - c->off[h->rec];
+		const int64_t g = c->off[h->rec] + (h->comp ? slen - 1 - (int64_t)h->szero : (int64_t)h->szero);
+		if (g >= c->lo && g < c->hi) {
+			if (k != i)
+				memmove(c->hits + k * c->stride, c->hits + i * c->stride, c->stride);
+			k++;
+		}
+	}
+	c->n = k;
+	return 0;
+}
+
+int gm_hits(const gm_ctx *c, const void **hits, size_t *n, size_t *stride)
+{
+	*hits = c->hits;
+	*n = c->n;
+	*stride = c->stride;
+	return 0;
+}
+
+int gm_stats(const gm_ctx *c, gm_scan_stats_t *out)
+{
+	memset(out, 0, sizeof *out);
+	out->n_hits = c->n;
+	return 0;
+}

@@ -1,0 +1,49 @@
+"""CPU: the HOST logic of the reference-side driver (rnamotif_b200/host/rm_gpu_main.c:
+batching of records, sharding of a batch into start ranges with the ordered merge,
+replay of the sink's tail through the reference's own score program and printer),
+byte for byte against the reference's stdout.
+
+oracle/_ref/rnamotif_hostcheck is that driver linked against oracle/gm_mock.c -- a
+stand-in for the C ABI whose candidates come from the oracle port -- instead of
+libgpumotif.so (test infrastructure; the product has no CPU search path).  The same
+command lines run on the device in tests/test_gpu_stdout.py."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import helpers
+
+BIN = os.path.join(helpers.REF, "rnamotif_hostcheck")
+DATA = os.path.join(helpers.REF, "data")
+MD5 = json.load(open(os.path.join(helpers.GOLDEN, "make_test_md5.json")))
+have = os.path.exists(BIN) and os.path.exists(os.path.join(DATA, "test", "gbrna.111.0.fastn"))
+
+
+def run(name, extra_env=None):
+    flags = ["-sh", "-context", "-Dctx_maxlen=5"] if name.endswith(".strict") else []
+    env = dict(os.environ, EFNDATA=os.path.join(DATA, "efndata"))
+    env.update(extra_env or {})
+    r = subprocess.run([BIN, *flags, "-descr", name + ".descr", "gbrna.111.0.fastn"],
+                       cwd=os.path.join(DATA, "test"), env=env, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode(errors="replace")[-2000:]
+    return r.stdout
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref/rnamotif_hostcheck not built")
+@pytest.mark.parametrize("name", ["trna", "trna.strict", "score.1", "score.2.strict", "efn.strict",
+                                  "sprintf", "bulge", "mp.ends.strict", "nanlin"])
+def test_host_driver_stdout_md5(name):
+    assert hashlib.md5(run(name)).hexdigest() == MD5[name]["md5"], f"{name}: stdout differs from the reference"
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref/rnamotif_hostcheck not built")
+@pytest.mark.parametrize("name", ["trna", "score.1"])
+def test_host_driver_small_batches_and_shards(name):
+    """Records split over many uploads (score state carried across batches) and every
+    batch cut into three start ranges whose candidate lists are merged before the
+    stateful score replay."""
+    out = run(name, {"GPUMOTIF_BATCH_NT": "300000", "GPUMOTIF_DEVICES": "0,0,0"})
+    assert hashlib.md5(out).hexdigest() == MD5[name]["md5"]
