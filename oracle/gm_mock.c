@@ -34,8 +34,14 @@ struct gm_ctx {
 	size_t n, stride;
 };
 
-static char mock_err[256] = "";
+static char mock_err[512] = "";
 const char *gm_last_error(void) { return mock_err; }
+/* error sink of gm_post.cpp (gm_prune_hits / gm_order_hits, linked as they are) */
+int gm_post_fail(const char *msg)
+{
+	snprintf(mock_err, sizeof mock_err, "%s", msg);
+	return -1;
+}
 
 int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 {

@@ -1,0 +1,275 @@
+// gm_post.cpp -- host-only post-filters of libgpumotif over hit records
+// (SURVEY section 8 f4): gm_prune_hits = the reference's rmprune, gm_order_hits =
+// the order rmfmt prints in.  Plain C++ (no CUDA): also linked into the CPU
+// checker of the host driver (oracle/Makefile: rnamotif_hostcheck).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "gpumotif.h"
+
+extern "C" int gm_post_fail(const char *msg); // sets gm_last_error(), returns -1
+
+static int fail(const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	return gm_post_fail(buf);
+}
+
+// ------------------------------------------------------------------ rmprune
+// src/rmprune.c on hit records; names follow the reference (B_SAME ...).
+namespace {
+enum { PB_UNDEF = -1, PB_SAME = 0, PB_LEFT = 1, PB_DOWN = 2, PB_DIFF = 3 };
+struct PruneDetail { int start, stop; };   // DETAIL_T, :68-71
+struct PruneHit {
+	int comp, start, stop;                 // BLOCK_T::b_comp, b_start, b_stop (:73-83)
+	std::vector<PruneDetail> det;
+};
+
+// wchlxrel, src/rmprune.c:700-741
+int prune_wchlxrel(int comp, const PruneDetail &dp, const PruneDetail &dp_2, const PruneDetail &dp1,
+	const PruneDetail &dp1_2)
+{
+	int lod, rod, lid, rid;
+	if (!comp) {
+		lod = dp1.start - dp.start;
+		rod = dp_2.stop - dp1_2.stop;
+		if (lod != rod)
+			return PB_DIFF;
+		lid = dp.stop - dp1.stop;
+		rid = dp1_2.start - dp_2.start;
+		if (lid != rid)
+			return PB_DIFF;
+	} else {
+		lod = dp.start - dp1.start;
+		rod = dp1_2.stop - dp_2.stop;
+		if (lod != rod)
+			return PB_DIFF;
+		lid = dp1.stop - dp.stop;
+		rid = dp_2.start - dp1_2.start;
+		if (lid != rid)
+			return PB_DIFF;
+	}
+	if (lod > 0)
+		return lid < 0 ? PB_DIFF : PB_DOWN;
+	if (lod == 0)
+		return lid < 0 ? PB_LEFT : lid == 0 ? PB_SAME : PB_DOWN;
+	return lid < 0 ? PB_DIFF : PB_LEFT;
+}
+
+// chkrel, src/rmprune.c:649-698
+int prune_chkrel(const gm_plan_t *pl, const PruneHit &b, const PruneHit &b1)
+{
+	int brel = PB_UNDEF, brel1 = PB_UNDEF;
+	for (int d = 0; d < pl->n_descr; d++) {
+		const gm_elem_t &e = pl->elems[d];
+		switch (e.type) {
+		case GM_H5:
+			brel1 = prune_wchlxrel(b.comp, b.det[d], b.det[e.mates[0]], b1.det[d], b1.det[e.mates[0]]);
+			break;
+		case GM_P5:
+		case GM_T1:
+		case GM_Q1: {
+			// otherhlxrel, :743-760: every strand at the same place, or different
+			brel1 = PB_SAME;
+			for (int k = -1; k < e.n_mates && k < 3; k++) {
+				const int x = k < 0 ? d : e.mates[k];
+				if (b.det[x].start != b1.det[x].start || b.det[x].stop != b1.det[x].stop) {
+					brel1 = PB_DIFF;
+					break;
+				}
+			}
+			break;
+		}
+		default:
+			brel1 = PB_SAME;
+			break;
+		}
+		if (brel1 == PB_DIFF)
+			return PB_DIFF;
+		else if (brel == PB_UNDEF)
+			brel = brel1;
+		else if (brel == PB_SAME)
+			brel = brel1;
+		else if (brel == PB_DOWN) {
+			if (brel1 == PB_LEFT)
+				return PB_DIFF;
+		} else if (brel == PB_LEFT) {
+			if (brel1 == PB_DOWN)
+				return PB_DIFF;
+		}
+	}
+	return brel;
+}
+
+// rezip_group, src/rmprune.c:400-441, over block[lo, lo + n_group)
+void prune_rezip(const gm_plan_t *pl, const std::vector<PruneHit> &blk, size_t lo, size_t n_group, uint8_t *keep)
+{
+	if (n_group < 2)
+		return;
+	for (size_t b = n_group - 1; b > 0; b--) {
+		if (!keep[lo + b])
+			continue;
+		for (size_t b1 = b; b1-- > 0;) {
+			if (!keep[lo + b1])
+				continue;
+			const int brel = prune_chkrel(pl, blk[lo + b], blk[lo + b1]);
+			if (brel == PB_DOWN)
+				keep[lo + b1] = 0;
+			else if (brel == PB_LEFT) {
+				keep[lo + b] = 0;
+				break;
+			}
+		}
+	}
+}
+
+// prune_block, src/rmprune.c:332-398
+void prune_block(const gm_plan_t *pl, const std::vector<PruneHit> &blk, uint8_t *keep)
+{
+	const size_t n = blk.size();
+	if (n < 2)
+		return;
+	size_t f_comp = 0;
+	while (f_comp < n && !blk[f_comp].comp)
+		f_comp++;
+	int start = blk[0].start, stop = blk[0].stop;
+	size_t lb = 0, b = 0;
+	for (; b < f_comp; b++) {
+		if (blk[b].start < start || blk[b].stop > stop) {
+			prune_rezip(pl, blk, lb, b - lb, keep);
+			start = blk[b].start;
+			stop = blk[b].stop;
+			lb = b;
+		}
+	}
+	prune_rezip(pl, blk, lb, b - lb, keep);
+	if (f_comp < n) {
+		start = blk[f_comp].start;
+		stop = blk[f_comp].stop;
+	}
+	for (lb = b = f_comp; b < n; b++) {
+		if (blk[b].start > start || blk[b].stop < stop) {
+			prune_rezip(pl, blk, lb, b - lb, keep);
+			start = blk[b].start;
+			stop = blk[b].stop;
+			lb = b;
+		}
+	}
+	prune_rezip(pl, blk, lb, b - lb, keep);
+}
+} // namespace
+
+extern "C" int gm_prune_hits(const gm_plan_t *plan, const void *hits, size_t n, size_t stride,
+	const int32_t *group, uint8_t *keep)
+{
+	if (plan == NULL || keep == NULL || (n > 0 && hits == NULL))
+		return fail("bad argument");
+	if (plan->magic != GM_PLAN_MAGIC || plan->version != GM_PLAN_VERSION)
+		return fail("not a plan of this library version");
+	const int ND = plan->n_descr;
+	if (ND < 1 || ND > GM_MAX_DESCR || stride < sizeof(gm_hit_hdr_t) + (size_t)ND * sizeof(gm_hit_el_t))
+		return fail("hit stride %zu too small for %d elements", stride, ND);
+	for (int d = 0; d < ND; d++) {
+		const gm_elem_t &e = plan->elems[d];
+		if ((e.type == GM_H5 || e.type == GM_P5 || e.type == GM_T1 || e.type == GM_Q1) &&
+		    (e.n_mates < 1 || e.mates[0] < 0 || e.mates[0] >= ND))
+			return fail("element %d: helix without a mate", d);
+	}
+	const uint8_t *base = static_cast<const uint8_t *>(hits);
+	std::vector<PruneHit> blk;
+	size_t blk_lo = 0;
+	auto flush = [&](size_t hi) {
+		prune_block(plan, blk, keep + blk_lo);
+		blk.clear();
+		blk_lo = hi;
+	};
+	for (size_t i = 0; i < n; i++) {
+		const gm_hit_hdr_t *h = reinterpret_cast<const gm_hit_hdr_t *>(base + i * stride);
+		const gm_hit_el_t *el = reinterpret_cast<const gm_hit_el_t *>(h + 1);
+		keep[i] = 1;
+		const int32_t g = group ? group[i] : (int32_t)h->rec;
+		if (i > 0) {
+			const gm_hit_hdr_t *hp = reinterpret_cast<const gm_hit_hdr_t *>(base + (i - 1) * stride);
+			const int32_t gp = group ? group[i - 1] : (int32_t)hp->rec;
+			// a new locus, or the reference's block array is full (BLOCK_SIZE, :82,183-186)
+			if (g != gp || blk.size() >= 1000)
+				flush(i);
+		}
+		// enter_block + getdetails, src/rmprune.c:762-818,619-647: the printed start
+		// is 1-based; on the complementary strand it counts down from the record's
+		// end (only differences matter, so the record length is left out)
+		PruneHit ph;
+		ph.comp = h->comp ? 1 : 0;
+		int len = 0;
+		for (int d = 0; d < ND; d++)
+			len += el[d].len;
+		ph.start = ph.comp ? -(int)el[0].off : (int)el[0].off + 1;
+		ph.stop = ph.comp ? ph.start - len + 1 : ph.start + len - 1;
+		ph.det.resize(ND);
+		int tlen = 0;
+		for (int d = 0; d < ND; d++) {
+			const int tl = el[d].len > 0 ? el[d].len : 1; // "." for an empty element
+			if (!ph.comp) {
+				ph.det[d].start = ph.start + tlen;
+				ph.det[d].stop = ph.det[d].start + tl - 1;
+			} else {
+				ph.det[d].start = ph.start - tlen;
+				ph.det[d].stop = ph.det[d].start - tl + 1;
+			}
+			tlen += tl;
+		}
+		blk.push_back(std::move(ph));
+	}
+	flush(n);
+	return 0;
+}
+
+extern "C" int gm_order_hits(const void *hits, size_t n, size_t stride, int n_descr, const double *score,
+	const int32_t *name_rank, const int64_t *rec_off, int n_rec, uint32_t *perm)
+{
+	if (perm == NULL || name_rank == NULL || rec_off == NULL || (n > 0 && hits == NULL) || n > 0xffffffffull)
+		return fail("bad argument");
+	if (n_descr < 1 || n_descr > GM_MAX_DESCR ||
+	    stride < sizeof(gm_hit_hdr_t) + (size_t)n_descr * sizeof(gm_hit_el_t))
+		return fail("hit stride %zu too small for %d elements", stride, n_descr);
+	const uint8_t *base = static_cast<const uint8_t *>(hits);
+	struct Key { double score; int32_t name; int32_t comp; int64_t pos; int32_t len; };
+	std::vector<Key> key(n);
+	for (size_t i = 0; i < n; i++) {
+		const gm_hit_hdr_t *h = reinterpret_cast<const gm_hit_hdr_t *>(base + i * stride);
+		const gm_hit_el_t *el = reinterpret_cast<const gm_hit_el_t *>(h + 1);
+		if ((int64_t)h->rec >= n_rec)
+			return fail("hit %zu: record %u outside the record table", i, h->rec);
+		Key &k = key[i];
+		k.score = score ? score[i] : 0.0;
+		k.name = name_rank[i];
+		k.comp = h->comp ? 1 : 0;
+		// print_match, src/find_motif.c:1838-1846
+		const int64_t slen = rec_off[h->rec + 1] - rec_off[h->rec];
+		k.pos = k.comp ? slen - el[0].off : (int64_t)el[0].off + 1;
+		k.len = 0;
+		for (int d = 0; d < n_descr; d++)
+			k.len += el[d].len;
+		perm[i] = (uint32_t)i;
+	}
+	std::stable_sort(perm, perm + n, [&](uint32_t a, uint32_t b) {
+		const Key &x = key[a], &y = key[b];
+		if (x.score != y.score)
+			return x.score > y.score; // -k 2rn
+		if (x.name != y.name)
+			return x.name < y.name;
+		if (x.comp != y.comp)
+			return x.comp < y.comp;
+		if (x.pos != y.pos)
+			return x.pos < y.pos;
+		return x.len < y.len;
+	});
+	return 0;
+}
+

@@ -13,7 +13,13 @@
  * or 0), GPUMOTIF_BATCH_NT (default 64 M), GPUMOTIF_STATS=1 prints per-batch
  * timings to stderr.  This in-process sharding stands in for the MPI file farm of
  * src/mrnamotif.c:105-192.
+ * GPUMOTIF_PRUNE=1: the output of `rnamotif | rmprune` in one pass -- the hits the
+ * score program accepts are captured instead of printed, gm_prune_hits() takes
+ * rmprune's decision on their records (src/rmprune.c), and only the kept ones are
+ * written.  (Hits a score program HOLDs and RELEASEs are printed by score.c itself
+ * and pass through unpruned.)
  */
+#define _GNU_SOURCE /* open_memstream */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,6 +38,7 @@ extern int gm_rm_compile(int, char *[]);
 extern int gm_flatten_plan(gm_plan_t *, char *, size_t);
 extern void GM_replay_strand(char[], char[], int, int, char[]);
 extern int GM_replay_hit(const gm_hit_hdr_t *, const gm_hit_el_t *);
+extern int GM_replay_hit_to(const gm_hit_hdr_t *, const gm_hit_el_t *, FILE *);
 
 typedef struct {
 	char *sid, *sdef;
@@ -101,6 +108,15 @@ int main(int argc, char *argv[])
 	int64_t *offs = NULL;
 	int n_recs, cap_recs = 0;
 	const char *ev;
+	/* GPUMOTIF_PRUNE: accepted hits of the batch, their text and their records */
+	int prune = 0;
+	FILE *cap = NULL;
+	char *cap_buf = NULL;
+	size_t cap_len = 0, n_acc = 0, acc_cap = 0;
+	size_t *acc_end = NULL;          /* end of hit k's text in the capture */
+	char *acc_hits = NULL;           /* their hit records, contiguous */
+	int32_t *acc_group = NULL;       /* rmprune's blocks: locus name up to the first '.' */
+	uint8_t *acc_keep = NULL;
 
 	gm_rm_compile(argc, argv);
 	if (gm_flatten_plan(&plan, err, sizeof err)) {
@@ -120,6 +136,8 @@ int main(int argc, char *argv[])
 		batch_nt = atoll(ev);
 	if ((ev = getenv("GPUMOTIF_STATS")) != NULL)
 		stats = atoi(ev);
+	if ((ev = getenv("GPUMOTIF_PRUNE")) != NULL)
+		prune = atoi(ev);
 	for (g = 0; g < n_gpus; g++)
 		if (gm_ctx_create(&ctxs[g], &plan, devices[g]))
 			die_gm("gm_ctx_create");
@@ -242,6 +260,14 @@ int main(int argc, char *argv[])
 		if (n_gpus > 1 && n_hits > 1)
 			qsort(order, n_hits, sizeof *order, hit_cmp);
 
+		if (prune) {
+			cap = open_memstream(&cap_buf, &cap_len);
+			if (cap == NULL) {
+				fprintf(stderr, "rnamotif_gpu: open_memstream failed\n");
+				exit(1);
+			}
+			n_acc = 0;
+		}
 		/* ---- replay the sink's tail in enumeration order ---- */
 		for (h = 0; h < n_hits;) {
 			const gm_hit_hdr_t *hdr = order[h];
@@ -268,9 +294,66 @@ int main(int argc, char *argv[])
 				hdr = order[h];
 				if (hdr->rec != rec || hdr->comp != comp)
 					break;
-				GM_replay_hit(hdr, (const gm_hit_el_t *)(hdr + 1));
+				if (!prune) {
+					GM_replay_hit(hdr, (const gm_hit_el_t *)(hdr + 1));
+					continue;
+				}
+				if (GM_replay_hit_to(hdr, (const gm_hit_el_t *)(hdr + 1), cap)) {
+					fflush(cap);
+					if (n_acc == acc_cap) {
+						acc_cap = acc_cap ? 2 * acc_cap : 1024;
+						acc_end = realloc(acc_end, acc_cap * sizeof *acc_end);
+						acc_hits = realloc(acc_hits, acc_cap * stride);
+						acc_group = realloc(acc_group, acc_cap * sizeof *acc_group);
+						acc_keep = realloc(acc_keep, acc_cap);
+						if (acc_end == NULL || acc_hits == NULL || acc_group == NULL || acc_keep == NULL) {
+							fprintf(stderr, "rnamotif_gpu: out of memory\n");
+							exit(1);
+						}
+					}
+					acc_end[n_acc] = cap_len;
+					memcpy(acc_hits + n_acc * stride, hdr, stride);
+					acc_group[n_acc] = (int32_t)rec;
+					n_acc++;
+				}
 			}
 			sb[rp->slen] = saved;
+		}
+		if (prune) {
+			size_t k, from = 0;
+			int32_t gid = 0;
+			fclose(cap);
+			/* rmprune's blocks are runs of hits whose locus names agree up to the
+			 * first '.' (getname, src/rmprune.c:312-330): number them */
+			for (k = 0; k < n_acc; k++) {
+				if (k > 0 && acc_group[k] != (int32_t)((const gm_hit_hdr_t *)(acc_hits + (k - 1) * stride))->rec) {
+					const char *a = recs[acc_group[k]].sid;
+					const char *b = recs[((const gm_hit_hdr_t *)(acc_hits + (k - 1) * stride))->rec].sid;
+					size_t la = strcspn(a, "."), lb = strcspn(b, ".");
+					if (la != lb || strncmp(a, b, la))
+						gid++;
+				}
+				acc_group[k] = gid; /* (the record is still in the copied hit header) */
+			}
+			if (gm_prune_hits(&plan, acc_hits, n_acc, stride, acc_group, acc_keep))
+				die_gm("gm_prune_hits");
+			for (k = 0; k < n_acc; k++) {
+				const char *t = cap_buf + from, *e = cap_buf + acc_end[k];
+				/* the first hit of the run carries print_match's "#RM" header lines:
+				 * rmprune passes them through whatever becomes of the hit */
+				while (t < e && *t != '>') {
+					const char *nl = memchr(t, '\n', (size_t)(e - t));
+					nl = nl ? nl + 1 : e;
+					fwrite(t, 1, (size_t)(nl - t), stdout);
+					t = nl;
+				}
+				if (acc_keep[k])
+					fwrite(t, 1, (size_t)(e - t), stdout);
+				from = acc_end[k];
+			}
+			free(cap_buf);
+			cap_buf = NULL;
+			cap_len = 0;
 		}
 		for (r = 0; r < n_recs; r++) {
 			free(recs[r].sid);

@@ -30,7 +30,9 @@ void GM_replay_strand(char sid[], char sdef[], int comp, int slen, char sbuf[])
 	fm_sbuf = sbuf;
 }
 
-int GM_replay_hit(const gm_hit_hdr_t *hdr, const gm_hit_el_t *els)
+/* fp: where print_match writes an accepted hit (stdout, or the driver's capture
+ * buffer when it post-filters the output) */
+int GM_replay_hit_to(const gm_hit_hdr_t *hdr, const gm_hit_el_t *els, FILE *fp)
 {
 	IDENT_T *h_idp;
 	STREL_T *stp;
@@ -59,6 +61,11 @@ int GM_replay_hit(const gm_hit_hdr_t *hdr, const gm_hit_el_t *els)
 	rm_lval->v_value.v_ival = len;
 	if (RM_score(fm_comp, fm_slen, fm_sbuf, &h_idp) == SA_REJECT)
 		return 0;
-	print_match(stdout, fm_sid, fm_comp, rm_n_descr, rm_descr, h_idp);
+	print_match(fp, fm_sid, fm_comp, rm_n_descr, rm_descr, h_idp);
 	return 1;
+}
+
+int GM_replay_hit(const gm_hit_hdr_t *hdr, const gm_hit_el_t *els)
+{
+	return GM_replay_hit_to(hdr, els, stdout);
 }

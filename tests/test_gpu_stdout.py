@@ -63,3 +63,19 @@ def test_stdout_with_sharded_scan(name):
     devs = "0,1,0" if torch.cuda.device_count() > 1 else "0,0,0"
     out = run(GPU_BIN, name, {"GPUMOTIF_DEVICES": devs, "GPUMOTIF_BATCH_NT": "1000000"})
     assert hashlib.md5(out).hexdigest() == MD5[name]["md5"]
+
+
+PRUNE_BIN = os.path.join(helpers.REF, "rmprune")
+
+
+@pytest.mark.skipif(not (have and os.path.exists(REF_BIN) and os.path.exists(PRUNE_BIN)),
+                    reason="reference binaries (rnamotif, rmprune) not built")
+@pytest.mark.parametrize("name", ["trna", "score.1"])
+def test_prune_option_equals_rnamotif_piped_through_rmprune(name):
+    """GPUMOTIF_PRUNE=1 (gm_prune_hits on the accepted hits' records) prints
+    byte for byte what `rnamotif ... | rmprune` prints.  The host side of this is also
+    checked without a GPU in tests/test_host_driver_cpu.py."""
+    ref = run(REF_BIN, name)
+    want = subprocess.run([PRUNE_BIN], input=ref, capture_output=True, timeout=600, check=True).stdout
+    got = run(GPU_BIN, name, {"GPUMOTIF_PRUNE": "1"})
+    assert got == want

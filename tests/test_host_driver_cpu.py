@@ -47,3 +47,25 @@ def test_host_driver_small_batches_and_shards(name):
     stateful score replay."""
     out = run(name, {"GPUMOTIF_BATCH_NT": "300000", "GPUMOTIF_DEVICES": "0,0,0"})
     assert hashlib.md5(out).hexdigest() == MD5[name]["md5"]
+
+
+REF_BIN = os.path.join(helpers.REF, "rnamotif")
+PRUNE_BIN = os.path.join(helpers.REF, "rmprune")
+
+
+@pytest.mark.skipif(not (have and os.path.exists(REF_BIN) and os.path.exists(PRUNE_BIN)),
+                    reason="oracle/_ref (rnamotif, rmprune, rnamotif_hostcheck) not built")
+@pytest.mark.parametrize("name,env", [("trna", {}), ("score.1", {}), ("mp.ends", {}), ("efn", {}),
+                                      ("trna", {"GPUMOTIF_BATCH_NT": "300000", "GPUMOTIF_DEVICES": "0,0"})])
+def test_prune_option_equals_rnamotif_piped_through_rmprune(name, env):
+    """GPUMOTIF_PRUNE=1: the driver captures the hits its score program accepts, lets
+    gm_prune_hits take rmprune's decision on their records and prints the kept ones --
+    byte for byte what `rnamotif ... | rmprune` prints (score.1 and mp.ends REJECT
+    candidates first; only printed hits take part in the pruning)."""
+    e = dict(os.environ, EFNDATA=os.path.join(DATA, "efndata"))
+    raw = subprocess.run([REF_BIN, "-descr", name + ".descr", "gbrna.111.0.fastn"], cwd=os.path.join(DATA, "test"),
+                         env=e, capture_output=True, timeout=600, check=True).stdout
+    want = subprocess.run([PRUNE_BIN], input=raw, capture_output=True, timeout=600, check=True).stdout
+    got = run(name, dict(env, GPUMOTIF_PRUNE="1"))
+    assert got == want
+    assert len(want) < len(raw) or name == "nanlin"
