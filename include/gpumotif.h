@@ -70,13 +70,20 @@ const char *gm_version(void);
 /* number of CUDA devices visible to the process (0 if none) */
 int gm_device_count(void);
 
-/* Validate the plan, select `device`, copy the plan to __constant__ memory.
- * Replaces RM_fm_init (src/find_motif.c:109). */
+/* Validate the plan, select `device`, give the context its own device copy of the
+ * plan (contexts share nothing: two contexts with different plans may scan on one
+ * device at the same time).  Replaces RM_fm_init (src/find_motif.c:109). */
 int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device);
 void gm_ctx_destroy(gm_ctx *c);
 
 /* Validate a plan without touching a device (host-side checks only). */
 int gm_plan_check(const gm_plan_t *plan);
+
+/* Describe what the library derives from a plan -- the per-search table, the
+ * level-0 filter chosen, look-ahead targets and probes -- as text into out[cap]
+ * (NUL-terminated, truncated if need be).  Host side, needs no device.  No
+ * counterpart in the reference (debugging aid, like its -d dump, src/rnamot.c:98). */
+int gm_plan_describe(const gm_plan_t *plan, char *out, size_t cap);
 
 /* Upload a batch of records given as the characters FN_fgetseq leaves in its
  * buffer (src/dbutil.c:42-128: letters only, any case, u or t): record r is

@@ -18,13 +18,16 @@
 
 namespace gm {
 
-__constant__ gm_plan_t c_plan;
-__constant__ DevSearch c_ds[GM_MAX_DESCR];
-__constant__ DevParams c_par;
 
 #define GM_REC_CACHE 30
 
+// every device function below takes the lane it works for; the staged plan hangs off it
+#define PV (*L.P)
+
 struct ScanArgs {
+	DevParams par;              // launch parameters (by value: they belong to this launch)
+	const gm_plan_t *plan;      // the context's own device copy of the plan ...
+	const DevSearch *ds;        // ... and of the derived per-search table
 	const uint8_t *packed;      // 4-bit codes, nucleotide g in byte g>>1, nibble g&1
 	int64_t total_nt;
 	const int64_t *rec_off;     // n_rec + 1 entries, device
@@ -135,12 +138,91 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		: "memory");
 }
 
+// ------------------------------------------------------------ plan staging
+
+// Shared memory stage_plan() carves, in bytes (the host sizes its launches with it).
+__host__ __device__ inline size_t plan_smem_bytes(const DevParams &par)
+{
+	size_t n = 0;
+	n += (sizeof(PlanView) + 15) & ~(size_t)15;
+	n += (par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
+	n += (par.n_descr * sizeof(gm_elem_t) + 15) & ~(size_t)15;
+	n += (par.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
+	n += (par.n_regex * sizeof(DevRegex) + 15) & ~(size_t)15;
+	n += ((size_t)par.n_scopes * 4 + 15) & ~(size_t)15;
+	n += ((size_t)par.n_lentab + 15) & ~(size_t)15;
+	n += (par.n_sites * sizeof(gm_site_t) + 15) & ~(size_t)15;
+	n += ((size_t)par.n_descr * 4 + 15) & ~(size_t)15;
+	return n;
+}
+
+struct StagedPlan {
+	PlanView *pv;
+	DevSearch *ds;
+	const gm_pairset_t *ps;
+	uint32_t *elmm;   // (minlen, maxlen) per element, packed (find_minlen / find_maxlen)
+};
+
+__device__ __forceinline__ void copy_words(void *dst, const void *src, int n_words, int tid, int nt)
+{
+	for (int i = tid; i < n_words; i += nt)
+		reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+}
+
+// Copy the parts of the plan this launch uses from the context's device copy into
+// shared memory at p; returns the first free byte.  The caller synchronises the block.
+__device__ __forceinline__ uint8_t *stage_plan(uint8_t *p, const ScanArgs &A, int tid, int nt, StagedPlan &sp)
+{
+	const DevParams &par = A.par;
+	const gm_plan_t *pl = A.plan;
+	PlanView *pv = reinterpret_cast<PlanView *>(p);         p += (sizeof(PlanView) + 15) & ~(size_t)15;
+	DevSearch *ds = reinterpret_cast<DevSearch *>(p);       p += (par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
+	gm_elem_t *el = reinterpret_cast<gm_elem_t *>(p);       p += (par.n_descr * sizeof(gm_elem_t) + 15) & ~(size_t)15;
+	gm_pairset_t *ps = reinterpret_cast<gm_pairset_t *>(p); p += (par.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
+	DevRegex *rx = reinterpret_cast<DevRegex *>(p);         p += (par.n_regex * sizeof(DevRegex) + 15) & ~(size_t)15;
+	int32_t *sc = reinterpret_cast<int32_t *>(p);           p += ((size_t)par.n_scopes * 4 + 15) & ~(size_t)15;
+	uint8_t *lt = p;                                        p += ((size_t)par.n_lentab + 15) & ~(size_t)15;
+	gm_site_t *si = reinterpret_cast<gm_site_t *>(p);       p += (par.n_sites * sizeof(gm_site_t) + 15) & ~(size_t)15;
+	uint32_t *elmm = reinterpret_cast<uint32_t *>(p);       p += ((size_t)par.n_descr * 4 + 15) & ~(size_t)15;
+	for (int i = tid; i < (int)(sizeof(DevParams) / 4); i += nt)
+		reinterpret_cast<uint32_t *>(&pv->par)[i] = reinterpret_cast<const uint32_t *>(&A.par)[i];
+	copy_words(ds, A.ds, par.n_searches * (int)(sizeof(DevSearch) / 4), tid, nt);
+	copy_words(el, pl->elems, par.n_descr * (int)(sizeof(gm_elem_t) / 4), tid, nt);
+	copy_words(ps, pl->pairsets, par.n_pairsets * (int)(sizeof(gm_pairset_t) / 4), tid, nt);
+	for (int r = 0; r < par.n_regex; r++)
+		copy_words(rx + r, &pl->regex[r], (int)(sizeof(DevRegex) / 4), tid, nt);
+	copy_words(sc, pl->scopes, par.n_scopes, tid, nt);
+	copy_words(lt, pl->lentab, (par.n_lentab + 3) / 4, tid, nt);
+	copy_words(si, pl->sites, par.n_sites * (int)(sizeof(gm_site_t) / 4), tid, nt);
+	for (int i = tid; i < par.n_descr; i += nt)
+		elmm[i] = pk16(pl->elems[i].minlen, pl->elems[i].maxlen);
+	if (tid == 0) {
+		pv->elems = el;
+		pv->pairsets = ps;
+		pv->regex = rx;
+		pv->scopes = sc;
+		pv->lentab = lt;
+		pv->sites = si;
+		pv->lctx = pl->lctx;
+		pv->rctx = pl->rctx;
+		pv->n_sites = par.n_sites;
+		pv->n_pairsets = par.n_pairsets;
+		pv->n_regex = par.n_regex;
+		pv->pad_ = 0;
+	}
+	sp.pv = pv;
+	sp.ds = ds;
+	sp.ps = ps;
+	sp.elmm = elmm;
+	return p;
+}
+
 // -------------------------------------------------------------- the sink
 
 __device__ __noinline__ uint32_t el_word_lite(const Lane &L, int d)
 {
-	const int s = c_par.elsrc[d];
-	const int type = c_plan.elems[d].type;
+	const int s = PV.par.elsrc[d];
+	const int type = PV.elems[d].type;
 	const int z = lo16(L_ZD(L, s));
 	if (type == GM_SS)
 		return pk16(z, lo16(L_FR(L, s, 0)) - z + 1);
@@ -149,17 +231,17 @@ __device__ __noinline__ uint32_t el_word_lite(const Lane &L, int d)
 		return pk16(z, hl);
 	return pk16(hi16(L_FR(L, s, 2)) - hl + 1, hl); // H3
 }
-__device__ __forceinline__ int m_off(const Lane &L, int d) { return lo16(el_word(L, d, c_par.lite != 0)); }
-__device__ __forceinline__ int m_len(const Lane &L, int d) { return hi16(el_word(L, d, c_par.lite != 0)); }
+__device__ __forceinline__ int m_off(const Lane &L, int d) { return lo16(el_word(L, d, PV.par.lite != 0)); }
+__device__ __forceinline__ int m_len(const Lane &L, int d) { return hi16(el_word(L, d, PV.par.lite != 0)); }
 
 // element type covering window-relative position p, or -1 (fm_window == UNDEF)
 __device__ __noinline__ int wtype(const Lane &L, int p)
 {
 	for (int d = 0; d < L.ND; d++) {
-		uint32_t w = el_word(L, d, c_par.lite != 0);
+		uint32_t w = el_word(L, d, PV.par.lite != 0);
 		int off = lo16(w), len = hi16(w);
 		if (len > 0 && p >= off && p < off + len)
-			return c_plan.elems[d].type;
+			return PV.elems[d].type;
 	}
 	return -1;
 }
@@ -174,14 +256,14 @@ __device__ __forceinline__ bool is_ss(const Lane &L, int p, bool undef_is_ss)
 __device__ __noinline__ bool sink_strict(const Lane &L)
 {
 	for (int d = 0; d < L.ND; d++) {
-		const gm_elem_t &e = c_plan.elems[d];
+		const gm_elem_t &e = PV.elems[d];
 		if (!e.strict)
 			continue;
 		if (e.type == GM_H5) {
 			int d3 = e.mates[0];
 			int h5_5 = m_off(L, d), h5_3 = h5_5 + m_len(L, d) - 1;
 			int h3_5 = m_off(L, d3), h3_3 = h3_5 + m_len(L, d3) - 1;
-			unsigned dup = c_plan.pairsets[e.pairset].duplex;
+			unsigned dup = PV.pairsets[e.pairset].duplex;
 			if (e.strict & GM_5STRICT) {
 				if (L.szero + h5_5 > 0 && L.szero + h3_3 < L.slen - 1) {
 					if (is_ss(L, h5_5 - 1, true) && is_ss(L, h3_3 + 1, true))
@@ -199,7 +281,7 @@ __device__ __noinline__ bool sink_strict(const Lane &L)
 			int t1_5 = m_off(L, d), t1_3 = t1_5 + m_len(L, d) - 1;
 			int t2_5 = m_off(L, d1), t2_3 = t2_5 + m_len(L, d1) - 1;
 			int t3_5 = m_off(L, d2), t3_3 = t3_5 + m_len(L, d2) - 1;
-			const gm_pairset_t &ps = c_plan.pairsets[e.pairset];
+			const gm_pairset_t &ps = PV.pairsets[e.pairset];
 			if ((e.strict & GM_5STRICT) && L.szero + t1_5 > 0) {
 				if (is_ss(L, t1_5 - 1, true) && is_ss(L, t2_3 + 1, false) && is_ss(L, t3_5 - 1, false))
 					if (triple(ps, L.sq[t1_5 - 1], L.sq[t2_3 + 1], L.sq[t3_5 - 1]))
@@ -216,7 +298,7 @@ __device__ __noinline__ bool sink_strict(const Lane &L)
 			int q2_5 = m_off(L, d1), q2_3 = q2_5 + m_len(L, d1) - 1;
 			int q3_5 = m_off(L, d2), q3_3 = q3_5 + m_len(L, d2) - 1;
 			int q4_5 = m_off(L, d3), q4_3 = q4_5 + m_len(L, d3) - 1;
-			const gm_pairset_t &ps = c_plan.pairsets[e.pairset];
+			const gm_pairset_t &ps = PV.pairsets[e.pairset];
 			if (e.strict & GM_5STRICT) {
 				if (L.szero + q1_5 > 0 && L.szero + q4_3 < L.slen - 1) {
 					if (is_ss(L, q1_5 - 1, true) && is_ss(L, q2_3 + 1, false) &&
@@ -240,33 +322,33 @@ __device__ __noinline__ bool sink_strict(const Lane &L)
 __device__ __noinline__ bool sink_context(const Lane &L, int ctx[4])
 {
 	ctx[0] = ctx[1] = ctx[2] = ctx[3] = -1;
-	if (c_plan.lctx.present) {
+	if (PV.lctx.present) {
 		int m0 = L.szero + m_off(L, 0);
-		int off = max(m0 - c_plan.lctx.maxlen, 0);
+		int off = max(m0 - PV.lctx.maxlen, 0);
 		int len = m0 - off;
 		ctx[0] = off;
 		ctx[1] = len;
-		if (len < c_plan.lctx.minlen)
+		if (len < PV.lctx.minlen)
 			return false;
-		if (c_plan.lctx.regex >= 0)
-			if (!rx_match(c_plan.regex[c_plan.lctx.regex], L.sq + (off - L.szero), len))
+		if (PV.lctx.regex >= 0)
+			if (!rx_match(PV.regex[PV.lctx.regex], L.sq + (off - L.szero), len))
 				return false;
 	}
-	if (c_plan.rctx.present) {
+	if (PV.rctx.present) {
 		int last = L.ND - 1;
 		int roff = L.szero + m_off(L, last) + m_len(L, last);
-		int end = min(roff + c_plan.rctx.maxlen, L.slen);
+		int end = min(roff + PV.rctx.maxlen, L.slen);
 		int len = end - roff;
 		ctx[2] = roff;
 		ctx[3] = len;
-		if (len < c_plan.rctx.minlen)
+		if (len < PV.rctx.minlen)
 			return false;
-		if (c_plan.rctx.regex >= 0) {
+		if (PV.rctx.regex >= 0) {
 			// the reference applies the pattern to the text that starts
 			// at the END of the context (:1745-1751), clipped by the NUL
 			// at slen
 			int avail = max(min(len, L.slen - end), 0);
-			if (!rx_match(c_plan.regex[c_plan.rctx.regex], L.sq + (end - L.szero), avail))
+			if (!rx_match(PV.regex[PV.rctx.regex], L.sq + (end - L.szero), avail))
 				return false;
 		}
 	}
@@ -276,8 +358,8 @@ __device__ __noinline__ bool sink_context(const Lane &L, int ctx[4])
 // chk_sites / chk_1_site, src/find_motif.c:1758-1808
 __device__ __noinline__ bool sink_sites(const Lane &L)
 {
-	for (int s = 0; s < c_plan.n_sites; s++) {
-		const gm_site_t &si = c_plan.sites[s];
+	for (int s = 0; s < PV.n_sites; s++) {
+		const gm_site_t &si = PV.sites[s];
 		int b[4];
 		for (int p = 0; p < si.n_pos; p++) {
 			int d = si.pos[p].elem, off = si.pos[p].offset, at;
@@ -293,7 +375,7 @@ __device__ __noinline__ bool sink_sites(const Lane &L)
 			}
 			b[p] = L.sq[at];
 		}
-		const gm_pairset_t &ps = c_plan.pairsets[si.pairset];
+		const gm_pairset_t &ps = PV.pairsets[si.pairset];
 		int rv = 0;
 		if (si.n_pos == 2)
 			rv = paired(ps.duplex, b[0], b[1]);
@@ -311,11 +393,11 @@ __device__ __noinline__ bool sink_sites(const Lane &L)
 __device__ __noinline__ void sink(Lane &L, const ScanArgs &A)
 {
 	int ctx[4];
-	if (c_par.strict_helices && !sink_strict(L))
+	if (PV.par.strict_helices && !sink_strict(L))
 		return;
 	if (!sink_context(L, ctx))
 		return;
-	if (c_plan.n_sites > 0 && !sink_sites(L))
+	if (PV.n_sites > 0 && !sink_sites(L))
 		return;
 	unsigned long long slot = atomicAdd(A.hit_count, 1ull);
 	uint32_t seq = L.seq++;
@@ -331,12 +413,12 @@ __device__ __noinline__ void sink(Lane &L, const ScanArgs &A)
 	h[6] = (uint32_t)ctx[2];
 	h[7] = (uint32_t)ctx[3];
 	for (int d = 0; d < L.ND; d++) {
-		const uint32_t el = el_word(L, d, c_par.lite != 0);
+		const uint32_t el = el_word(L, d, PV.par.lite != 0);
 		int mpr, mm;
-		if (c_par.lite) {
+		if (PV.par.lite) {
 			// counts live in the frames: a helix head keeps its mispairs, an ss its mismatches
-			const int f1 = lo16(L_FR(L, c_par.elsrc[d], 1));
-			if (c_plan.elems[d].type == GM_SS) {
+			const int f1 = lo16(L_FR(L, PV.par.elsrc[d], 1));
+			if (PV.elems[d].type == GM_SS) {
 				mpr = 0;
 				mm = f1;
 			} else {
@@ -360,7 +442,7 @@ __device__ __forceinline__ int chk_seq5(Lane &L, const DevSearch &S, int off, in
 {
 	// chk_seq on the head element, src/find_motif.c:1810-1824; n_mm is what it
 	// leaves in s_n_mismatches
-	const gm_regex_t &rx = c_plan.regex[S.rx5];
+	const DevRegex &rx = PV.regex[S.rx5];
 	n_mm = 0;
 	if (S.mm5 > 0)
 		return rx_match_mm(rx, L.sq + off, len, S.mm5, &n_mm);
@@ -372,8 +454,8 @@ __device__ __forceinline__ int chk_seq5(Lane &L, const DevSearch &S, int off, in
 // goes to the element's counter word, which is what the sink reports.
 __device__ __noinline__ int chk_seq_el(Lane &L, int d, int off, int len)
 {
-	const gm_elem_t &e = c_plan.elems[d];
-	const gm_regex_t &rx = c_plan.regex[e.regex];
+	const gm_elem_t &e = PV.elems[d];
+	const DevRegex &rx = PV.regex[e.regex];
 	if (e.mismatch > 0) {
 		int n_mm;
 		const int ok = rx_match_mm(rx, L.sq + off, len, e.mismatch, &n_mm);
@@ -404,9 +486,9 @@ __device__ __forceinline__ bool wx_next(const Lane &L, const DevSearch &S, int s
 		if (chk) {
 			if (hl >= S.minlen &&
 			    !(!lbpr && (S.ends & GM_3PAIRED)) &&
-			    !(S.pfrac && mpr > c_plan.lentab[S.lentab + hl]) &&
-			    !(S.rx5 >= 0 && !rx_match(c_plan.regex[S.rx5], L.sq + s5, hl)) &&
-			    !(S.rx3 >= 0 && !rx_match(c_plan.regex[S.rx3], L.sq + s3 - hl + 1, hl)))
+			    !(S.pfrac && mpr > PV.lentab[S.lentab + hl]) &&
+			    !(S.rx5 >= 0 && !rx_match(PV.regex[S.rx5], L.sq + s5, hl)) &&
+			    !(S.rx3 >= 0 && !rx_match(PV.regex[S.rx3], L.sq + s3 - hl + 1, hl)))
 				return true;
 		}
 		if (s3 - hl + 1 < s3lim || hl >= S.maxlen)
@@ -446,7 +528,7 @@ __device__ __noinline__ bool wx_next_mm(Lane &L, const DevSearch &S, int s5, int
 		if (chk) {
 			if (hl >= S.minlen &&
 			    !(!lbpr && (S.ends & GM_3PAIRED)) &&
-			    !(S.pfrac && mpr > c_plan.lentab[S.lentab + hl]) &&
+			    !(S.pfrac && mpr > PV.lentab[S.lentab + hl]) &&
 			    !(S.rx5 >= 0 && !chk_seq_el(L, S.d, s5, hl)) &&
 			    !(S.rx3 >= 0 && !chk_seq_el(L, S.d3, s3 - hl + 1, hl))) {
 				more = true;
@@ -499,7 +581,7 @@ __device__ __noinline__ int pk_maxlen(const Lane &L, const uint32_t *elmm, int f
 __device__ __noinline__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int s5, int s3, int s5hi, int s5lo,
 	int *hlen, int *n_mpr)
 {
-	const gm_elem_t &e3 = c_plan.elems[d3];
+	const gm_elem_t &e3 = PV.elems[d3];
 	const int b3 = L.sq[s3];
 	for (int s = s5hi; s >= s5lo; s--) {
 		int hl, mpr, l_pr;
@@ -523,7 +605,7 @@ __device__ __noinline__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int
 			return false;
 		if (hl < S.minlen || hl > S.maxlen)
 			return false;
-		if (S.pfrac && mpr > c_plan.lentab[S.lentab + hl])
+		if (S.pfrac && mpr > PV.lentab[S.lentab + hl])
 			return false;
 		if (S.rx5 >= 0 && !chk_seq_el(L, S.d, s5, hl))
 			return false;
@@ -539,10 +621,10 @@ __device__ __noinline__ bool match_phlx(Lane &L, const DevSearch &S, int d3, int
 // match_triplex, src/find_motif.c:1183-1232
 __device__ __noinline__ bool match_triplex(Lane &L, const DevSearch &S, int dd1, int s1, int s2, int s3, int tlen, int *n_mpr)
 {
-	const gm_elem_t &e = c_plan.elems[S.d];
-	const gm_elem_t &e1 = c_plan.elems[dd1];
+	const gm_elem_t &e = PV.elems[S.d];
+	const gm_elem_t &e1 = PV.elems[dd1];
 	const gm_pairset_t &ps = L.ps[e.pairset];
-	const int mplim = c_plan.lentab[e.mptab + tlen];
+	const int mplim = PV.lentab[e.mptab + tlen];
 	int mpr, l_pr;
 	if (triple(ps, L.sq[s1], L.sq[s2], L.sq[s3 - tlen + 1])) {
 		mpr = 0; l_pr = 1;
@@ -570,10 +652,10 @@ __device__ __noinline__ bool match_triplex(Lane &L, const DevSearch &S, int dd1,
 // the loop header resets the mispair count (:1260)
 __device__ __noinline__ bool match_4plex(Lane &L, int dd1, int dd2, int s1, int s2, int s3, int s4, int qlen, int *n_mpr)
 {
-	const gm_elem_t &e1 = c_plan.elems[dd1];
-	const gm_elem_t &e2 = c_plan.elems[dd2];
+	const gm_elem_t &e1 = PV.elems[dd1];
+	const gm_elem_t &e2 = PV.elems[dd2];
 	const gm_pairset_t &ps = L.ps[e1.pairset];
-	const int mplim = c_plan.lentab[e1.mptab + qlen];
+	const int mplim = PV.lentab[e1.mptab + qlen];
 	int mpr, l_pr;
 	if (quad(ps, L.sq[s1 + qlen - 1], L.sq[s2], L.sq[s3], L.sq[s4 - qlen + 1])) {
 		l_pr = 1;
@@ -603,31 +685,31 @@ __device__ __noinline__ bool match_4plex(Lane &L, int dd1, int dd2, int s1, int 
 // upd_pksearches, src/find_motif.c:667-701
 __device__ __noinline__ void upd_pksearches(Lane &L, int d, int h5, int h3, int hlen)
 {
-	const gm_elem_t &e = c_plan.elems[d];
+	const gm_elem_t &e = PV.elems[d];
 	const int d3 = e.mates[0];
-	const gm_elem_t &e3 = c_plan.elems[d3];
+	const gm_elem_t &e3 = PV.elems[d3];
 	int id;
 	if (e.scope > 0) {
-		id = c_plan.elems[c_plan.scopes[e.scopes + e.scope - 1]].inner;
+		id = PV.elems[PV.scopes[e.scopes + e.scope - 1]].inner;
 		if (id >= 0) {
-			int si = c_plan.elems[id].searchno;
+			int si = PV.elems[id].searchno;
 			L_ZD(L, si) = pk16(lo16(L_ZD(L, si)), h5 - 1);
 		}
 	}
 	id = e.inner;
 	if (id >= 0) {
-		int si = c_plan.elems[id].searchno;
+		int si = PV.elems[id].searchno;
 		L_ZD(L, si) = pk16(h5 + hlen, hi16(L_ZD(L, si)));
 	}
-	id = c_plan.elems[c_plan.scopes[e3.scopes + e3.scope - 1]].inner;
+	id = PV.elems[PV.scopes[e3.scopes + e3.scope - 1]].inner;
 	if (id >= 0) {
-		int si = c_plan.elems[id].searchno;
+		int si = PV.elems[id].searchno;
 		L_ZD(L, si) = pk16(lo16(L_ZD(L, si)), h3 - hlen);
 	}
 	if (e3.scope < e3.n_scopes - 1) {
 		id = e3.inner;
 		if (id >= 0) {
-			int si = c_plan.elems[id].searchno;
+			int si = PV.elems[id].searchno;
 			L_ZD(L, si) = pk16(h3 + 1, hi16(L_ZD(L, si)));
 		}
 	}

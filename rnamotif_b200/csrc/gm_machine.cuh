@@ -316,22 +316,54 @@ __device__ __noinline__ uint64_t wc_mask_rev(const PairBits &pb, const uint8_t *
 }
 
 // Tail look-ahead (DevSearch::lk_t): with helix S chosen as (s5, s3, hl), can the
-// last helix group T of its interior chain form at all?  T ends at
-// e = s3 - hl - lk_off and begins somewhere in [e - maxglen + 1, e - minglen + 1],
-// not before the interior does.  Pure pruning: a false answer means no
+// helix T whose 3' strand ends lk_off nucleotides before S's 3' strand form at all?
+// T ends at e = s3 - hl - lk_off and begins somewhere in [e - dhi, e - dlo], not
+// before S's 5' strand ends.  Pure pruning: a false answer means no
 // assignment of the interior reaches the hit sink.
 __device__ __forceinline__ bool tail_feasible(const PairBits &pb, const uint8_t *sq, int strand, int sqbase,
 	const DevSearch &S, const DevSearch &T, int s5, int s3, int hl)
 {
 	const int e = s3 - hl - S.lk_off;
-	int zhi = e - T.minglen + 1;
-	const int zlo = max(e - T.maxglen + 1, s5 + hl);
+	int zhi = e - T.dlo;
+	const int zlo = max(e - T.dhi, s5 + hl);
 	for (; zhi >= zlo; zhi -= 64) {
 		const int l0 = max(zlo, zhi - 63);
 		if (wc_mask_rev(pb, sq, strand, sqbase, T.dupi_t, T.flt, e, l0, zhi - l0 + 1) != 0)
 			return true;
 	}
 	return false;
+}
+
+// Forward look-ahead: can helix T, whose 5' strand starts at zt, have any span end
+// in [zt + dlo, min(zt + dhi, bound)] at which its first pairs form?
+#define GM_LOOK_FWD(any, T, zt, bound)                                   \
+	do {                                                                 \
+		int f_ = min((bound), (zt) + (T).dhi);                           \
+		const int l_ = (zt) + (T).dlo;                                   \
+		(any) = false;                                                   \
+		for (; f_ >= l_ && !(any); f_ -= 64) {                           \
+			const int l0_ = max(l_, f_ - 63);                            \
+			(any) = GM_MASK((T), (zt), l0_, f_ - l0_ + 1) != 0;          \
+		}                                                                \
+	} while (0)
+
+// Probes (DevSearch::probe): fixed-length single strands with seq= whose place follows
+// from the helix (s5, s3, hl) just chosen.  wend = last position of the window.
+__device__ __noinline__ bool probes_ok(const Lane &L, const DevSearch &S, int s5, int s3, int hl, int wend)
+{
+	for (int i = 0; i < S.n_probe; i++) {
+		const unsigned pr = S.probe[i];
+		const int anchor = pr & 3, off = (pr >> 2) & 1023, len = (pr >> 12) & 255;
+		const int rxi = (pr >> 20) & 31, mm = (pr >> 25) & 15;
+		const int pos = anchor == 0 ? s5 + hl + off : anchor == 1 ? s3 + 1 + off : s3 - hl + 1 - off - len;
+		if (pos < 0 || pos + len - 1 > wend)
+			return false;
+		const DevRegex &rx = PV.regex[rxi];
+		int n_mm;
+		if (mm > 0 ? !rx_match_mm(rx, L.sq + pos, len, mm, &n_mm) : !rx_match(rx, L.sq + pos, len))
+			return false;
+	}
+	return true;
 }
 
 // MODE 0: fused -- prefilter and machine in one kernel (works for every plan).
@@ -358,29 +390,31 @@ __global__ void gm_search_kernel(const ScanArgs A)
 {
 	constexpr bool SIEVE = PF == 2; // word-parallel level-0 sieve instead of the per-start prefilter
 	// literal prefilter: per start (PF == 1) or as one more term of the sieve
-	const bool LIT = PF == 1 || (SIEVE && c_par.lit_present != 0);
+	const bool LIT = PF == 1 || (SIEVE && A.par.lit_present != 0);
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, nt = blockDim.x;
 	const int lane = tid & 31, warp = tid >> 5;
-	const int NS = c_par.n_searches, ND = c_par.n_descr;
-	const int W = c_par.w_winsize, H = c_par.halo, TILE = c_par.tile;
+	const int NS = A.par.n_searches, ND = A.par.n_descr;
+	const int W = A.par.w_winsize, H = A.par.halo, TILE = A.par.tile;
 	const int Lbytes = (TILE + 2 * H + 31) & ~31;          // nucleotides staged per tile (whole bitset words)
 	const int stage_bytes = ((Lbytes >> 1) + 32 + 15) & ~15; // packed staging (+ alignment slack)
 	const int nwb = ((Lbytes + 31) >> 5) + 4;
-	const int n_dups = c_par.n_dups;
+	const int n_dups = A.par.n_dups;
 	const int NBUF = MODE == 0 ? 2 : 1;
 
-	// carve shared memory (mirrors smem_need() on the host): plan tables shared
+	// carve shared memory (mirrors smem_need() on the host): the staged plan shared
 	// by the block, then one private region per warp, then the lane state
 	const int nwarps = nt >> 5;
 	const size_t pb_bytes = (((size_t)2 * n_dups * 4 * nwb * 4) + 15) & ~(size_t)15;
 	const size_t lit_bytes = LIT ? (((size_t)2 * nwb * 4) + 15) & ~(size_t)15 : 0;
 	const size_t buf_bytes = 2 * (size_t)Lbytes + pb_bytes + (GM_REC_CACHE + 2) * 8 + lit_bytes;
-	const size_t warp_bytes = 16 + (size_t)stage_bytes + NBUF * buf_bytes + GM_QCAP * 2 + (SIEVE ? ((6 * (size_t)nwb * 4 + 15) & ~(size_t)15) : 0);
-	uint8_t *p = smem_raw;
-	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
-	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
-	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
+	const bool CHAIN = SIEVE && A.par.chain > 0;
+	const size_t warp_bytes = 16 + (size_t)stage_bytes + NBUF * buf_bytes + GM_QCAP * 2 + (SIEVE ? ((6 * (size_t)nwb * 4 + 15) & ~(size_t)15) : 0) +
+		(CHAIN ? ((6 * (size_t)nwb * 4 + 15) & ~(size_t)15) : 0);
+	StagedPlan sp;
+	uint8_t *p = stage_plan(smem_raw, A, tid, nt, sp);
+	DevSearch *sm_ds = sp.ds;
+	uint32_t *sm_elmm = sp.elmm;
 	uint64_t *sm_litB = reinterpret_cast<uint64_t *>(p);       p += LIT ? 16 * 8 : 0; // literal prefilter class masks
 	uint8_t *wp = p + (size_t)warp * warp_bytes;               p += (size_t)nwarps * warp_bytes;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
@@ -394,30 +428,29 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	uint32_t *sv_E = reinterpret_cast<uint32_t *>(myq + GM_QCAP);
 	uint32_t *sv_K = sv_E + 2 * nwb;
 	uint32_t *sv_K2 = sv_K + 2 * nwb; // starts at which the helix FOLLOWING that first helix can form (pf_deep == 2)
-	const bool deep = SIEVE && c_par.pf_deep != 0;
+	// composition chain (DevParams::chain): two feasibility bitsets per strand
+	// (ping-pong) and the bitset of positions whose base the current element allows
+	uint32_t *ch_F = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(sv_E) + (SIEVE ? ((6 * (size_t)nwb * 4 + 15) & ~(size_t)15) : 0));
+	uint32_t *ch_OK = ch_F + 4 * nwb;
+	const uint32_t *ch_F0 = ch_F; // the finished chain: bit p <=> the whole descriptor can be laid out from p
+	const bool deep = SIEVE && A.par.pf_deep != 0;
 	const int sv_nws = ((TILE - 1) >> 5) + 2;               // sieve words per strand
 	const int sv_npass = (A.strands * sv_nws + 31) >> 5;
 
-	// stage the hot plan tables
-	for (int i = tid; i < NS * (int)(sizeof(DevSearch) / 4); i += nt)
-		reinterpret_cast<uint32_t *>(sm_ds)[i] = reinterpret_cast<const uint32_t *>(c_ds)[i];
-	for (int i = tid; i < c_plan.n_pairsets * (int)(sizeof(gm_pairset_t) / 4); i += nt)
-		reinterpret_cast<uint32_t *>(sm_ps)[i] = reinterpret_cast<const uint32_t *>(c_plan.pairsets)[i];
-	for (int i = tid; i < ND; i += nt)
-		sm_elmm[i] = pk16(c_plan.elems[i].minlen, c_plan.elems[i].maxlen);
 	if (LIT && tid < 16)
-		sm_litB[tid] = c_plan.regex[c_par.lit_rx].B[tid];
+		sm_litB[tid] = A.plan->regex[A.par.lit_rx].B[tid];
 	if (lane == 0)
 		mbar_init(&sm->bar, 1);
 
 	Lane L;
+	L.P = sp.pv;
 	L.st = sm_state + tid;
 	L.nt = nt;
 	L.ds = sm_ds;
-	L.ps = sm_ps;
+	L.ps = sp.ps;
 	L.NS = NS;
 	L.ND = ND;
-	L.el_base = NS + c_par.frame_words;
+	L.el_base = NS + A.par.frame_words;
 	L.sq = bufs;
 	L.szero = L.slen = L.comp = 0;
 	L.rec = 0;
@@ -453,7 +486,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	int rec0_len = 0;
 	int work_next = 0;
 	const int n_work = A.strands * TILE;
-	const int refill_min = c_par.refill_min;
+	const int refill_min = A.par.refill_min;
 
 	// per lane: where the start it is enumerating lives
 	int sqbase = 0, strand = 0, mybuf = 0;
@@ -539,7 +572,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			const int st = sd >= n_dups, dd = st ? sd - n_dups : sd;
 			if (dd == 0)
 				continue;
-			const unsigned dup = c_par.dups[dd];
+			const unsigned dup = A.par.dups[dd];
 			const uint32_t *bs_ = pbw + (size_t)(st * n_dups) * 4 * nwb;
 			uint32_t *out = pbw + (size_t)(st * n_dups + dd) * 4 * nwb;
 			for (int x = 0; x < 4; x++) {
@@ -562,8 +595,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			// k accepts base x if its class mask says so, and any nucleotide that is not
 			// plain a/c/g/t counts as accepted -- a superset of the true occurrences
 			// (survivors take the exact tests in the machine).
-			const int len = c_par.lit_len, l_mm = c_par.lit_mm;
-			const uint64_t dot = c_plan.regex[c_par.lit_rx].dot;
+			const int len = A.par.lit_len, l_mm = A.par.lit_mm;
+			const uint64_t dot = PV.regex[A.par.lit_rx].dot;
 			const uint64_t sel0 = sm_litB[1], sel1 = sm_litB[2], sel2 = sm_litB[4], sel3 = sm_litB[8];
 			for (int idx = lane; idx < 2 * nwb; idx += 32) {
 				const int st = idx >= nwb, w = idx - st * nwb;
@@ -643,7 +676,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		szero = comp ? slen - 1 - pos : pos;
 		idx = (int)(g - lo);
 		// RM_find_motif searches szero in [0, slen - rm_dminlen], src/find_motif.c:184-205
-		return slen - szero >= c_par.dminlen;
+		return slen - szero >= A.par.dminlen;
 	};
 
 	// level-0 prefilter of start item q.  v0/have_v0: the candidate mask of
@@ -664,8 +697,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		if (LIT) {
 			// the literal must begin lmin..lmax nucleotides after the start and end
 			// inside the window
-			const int l = c_par.lit_lmin;
-			int h = min(c_par.lit_lmax, dl + 1 - c_par.lit_len);
+			const int l = A.par.lit_lmin;
+			int h = min(A.par.lit_lmax, dl + 1 - A.par.lit_len);
 			bool any = false;
 			const uint32_t *set = sm_lit + comp * nwb;
 			for (; h >= l && !any; h -= 64) {
@@ -676,36 +709,29 @@ __global__ void gm_search_kernel(const ScanArgs A)
 			if (!any)
 				return false;
 		}
-		if (c_par.pf_search >= 0) {
+		if (A.par.pf_search >= 0) {
 			// any span end at all for the first helix of the descriptor?  (It is
 			// search 0, or follows fixed-length single strands, so its 5' start
 			// pz is known.)
-			const DevSearch &SP = sm_ds[c_par.pf_search];
-			const int pz = c_par.pf_z;
-			int fsd, lsd;
-			if (SP.kind == K_PK) {
-				fsd = dl;
-				lsd = pz + 2 * SP.minlen - 1;
-			} else {
-				fsd = min(dl, pz + SP.maxglen - 1);
-				lsd = pz + SP.minglen - 1;
-			}
+			const DevSearch &SP = sm_ds[A.par.pf_search];
+			const int pz = A.par.pf_z;
+			const int fsd = min(dl, pz + SP.dhi), lsd = pz + SP.dlo;
 			bool any = false;
 			for (int hi = fsd; hi >= lsd && !any; hi -= 64) {
 				const int l0 = max(lsd, hi - 63);
 				const uint64_t v = wc_mask(pb, sq, comp, base, SP.dupi, SP.flt, pz, l0, hi - l0 + 1);
 				any = v != 0;
-				if (hi == fsd && l0 == lsd && SP.kind != K_PK && c_par.pf_search == 0) {
+				if (hi == fsd && l0 == lsd && SP.kind != K_PK && A.par.pf_search == 0) {
 					v0 = v;
 					have_v0 = 1;
 				}
 			}
 			pass = any;
 		}
-		if (pass && S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
+		if (pass && S0.rx5 >= 0 && S0.mm5 == 0 && !PV.regex[S0.rx5].eol) {
 			// a seq= without '$' that cannot match the longest
 			// placement cannot match a shorter one
-			pass = rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
+			pass = rx_match(PV.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
 		}
 		return pass;
 	};
@@ -718,19 +744,87 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		if (!locate(q, comp, idx, rec, slen, szero))
 			return false;
 		const DevSearch &S0 = sm_ds[0];
-		if (S0.rx5 >= 0 && S0.mm5 == 0 && !c_plan.regex[S0.rx5].eol) {
+		if (S0.rx5 >= 0 && S0.mm5 == 0 && !PV.regex[S0.rx5].eol) {
 			const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
 			const int dl = min(W, slen - szero) - 1;
-			return rx_match(c_plan.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
+			return rx_match(PV.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)) != 0;
 		}
 		return true;
+	};
+
+	// ---- composition chain (a sieve term) ----
+	// Going through the descriptor's elements from the last to the first, F(p) = "this
+	// element and everything behind it can be laid out contiguously from p, every
+	// helix strand made of bases its pair table can pair at all (up to the mispair
+	// budget, end positions as `ends` demands)".  Single strands and strands any base
+	// can sit in only dilate F by their length range.  Equal strand lengths and the
+	// pairing itself are left to the machine: a superset of the starts with a
+	// candidate, computed for 32 starts per word.  One word per lane.
+	auto chain_build = [&]() {
+		const int nw = Lbytes >> 5;
+		uint32_t *Fa = ch_F, *Fb = ch_F + 2 * nwb;
+		for (int i = lane; i < 2 * nwb; i += 32)
+			Fa[i] = ~0u; // behind the last element anything goes
+		__syncwarp();
+		const uint32_t *pbw = pb.base;
+		for (int c = 0; c < A.par.chain; c++) {
+			const unsigned w0 = A.par.chain_w0[c], w1 = A.par.chain_w1[c];
+			const int mn = w0 & 4095, mx = (w0 >> 12) & 4095, cm = (w0 >> 24) & 15;
+			const bool both = (w0 >> 28) & 1, con = (w0 >> 29) & 1;
+			if (con) {
+				for (int i = lane; i < 2 * nwb; i += 32) {
+					const int st = i >= nwb, w = i - st * nwb;
+					const uint32_t *Bs = pbw + (size_t)(st * n_dups) * 4 * nwb;
+					ch_OK[i] = ((cm & 1) ? Bs[w] : 0u) | ((cm & 2) ? Bs[nwb + w] : 0u) | ((cm & 4) ? Bs[2 * nwb + w] : 0u) |
+						((cm & 8) ? Bs[3 * nwb + w] : 0u);
+				}
+				__syncwarp();
+			}
+			for (int i = lane; i < 2 * nwb; i += 32) {
+				const int st = i >= nwb, w = i - st * nwb;
+				uint32_t out = ~0u; // beyond the staged range: unknown, so feasible
+				if (w < nw && st < A.strands) {
+					const uint32_t *Fn = Fa + st * nwb;
+					const int q0 = w << 5;
+					out = 0;
+					if (!con) {
+						for (int len = mn; len <= mx && out != ~0u; len++)
+							out |= bits32(Fn, min(q0 + len, Lbytes));
+					} else {
+						const uint32_t *OK = ch_OK + st * nwb;
+						uint32_t a0 = ~0u, a1 = ~0u, a2 = ~0u; // at most 0 / 1 / 2 positions so far whose base is not allowed
+						const uint32_t ok0 = OK[w];
+						for (int k = 0; k < mx; k++) {
+							const uint32_t m = bits32(OK, min(q0 + k, Lbytes));
+							a2 = (a2 & m) | a1;
+							a1 = (a1 & m) | a0;
+							a0 &= m;
+							const int hl = k + 1;
+							if (hl >= mn) {
+								const int b = (w1 >> (2 * (hl - mn))) & 3;
+								uint32_t okh = b == 0 ? a0 : b == 1 ? a1 : b == 2 ? a2 : ~0u;
+								if (both && b != 3)
+									okh &= ok0 & m;
+								out |= okh & bits32(Fn, min(q0 + hl, Lbytes));
+							}
+						}
+					}
+				}
+				Fb[i] = out;
+			}
+			__syncwarp();
+			uint32_t *t_ = Fa;
+			Fa = Fb;
+			Fb = t_;
+		}
+		ch_F0 = Fa;
 	};
 
 	// ---- the sieve (PF == 2), shared by the fused and the prefilter-only kernel ----
 	// look-ahead bitsets for the current tile, one word per lane: over the range
 	// of positions the main pass can ask about
 	auto sieve_aux = [&]() {
-		const DevSearch &SP = sm_ds[c_par.pf_search];
+		const DevSearch &SP = sm_ds[A.par.pf_search];
 		const int nw = Lbytes >> 5;
 		for (int i = lane; i < 2 * nwb; i += 32) {
 			sv_E[i] = 0;
@@ -740,16 +834,16 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		__syncwarp();
 		const int nv = (int)(gB - gA);
 		for (int st = 0; st < A.strands; st++) {
-			const int zlo = (st ? Lbytes - H - nv : H) + c_par.pf_z, zhi = zlo + nv - 1; // helix starts of this tile
+			const int zlo = (st ? Lbytes - H - nv : H) + A.par.pf_z, zhi = zlo + nv - 1; // helix starts of this tile
 			if (SP.lk_t >= 0) {
 				// ends asked about: zb + d - hl - lk_off; the helices that end there start
 				// up to maxglen - 1 earlier
 				const DevSearch &T = sm_ds[SP.lk_t];
-				const int lo_ = max(zlo + SP.minglen - 1 - SP.maxlen - SP.lk_off - (T.maxglen - 1), 0);
-				const int hi_ = min(zhi + SP.maxglen - 1 - SP.minlen - SP.lk_off - (T.minglen - 1), Lbytes - 1);
+				const int lo_ = max(zlo + SP.dlo - SP.maxlen - SP.lk_off - T.dhi, 0);
+				const int hi_ = min(zhi + SP.dhi - SP.minlen - SP.lk_off - T.dlo, Lbytes - 1);
 				uint32_t *E = sv_E + st * nwb;
 				for (int w = (lo_ >> 5) + lane; w <= (hi_ >> 5) && w < nw; w += 32)
-					sieve_word_main(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
+					sieve_word_main(pb, st, T.dupi, T.flt, w, T.dlo, T.dhi,
 						[&](int d, uint32_t f) -> uint32_t {
 							// the helix that starts at bit t ends at t + d
 							const int q = (w << 5) + d, sh = q & 31;
@@ -766,22 +860,22 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				const DevSearch &T = sm_ds[SP.kid_t];
 				const int lo_ = zlo + SP.minlen + SP.kid_off;
 				const int hi_ = min(zhi + SP.maxlen + SP.kid_off + 31, Lbytes - 1);
-				const bool has_k2 = c_par.pf_deep == 2;
+				const bool has_k2 = A.par.pf_deep == 2;
 				const uint32_t *K2 = sv_K2 + st * nwb;
 				if (has_k2) {
 					// the helix after the first interior helix starts sib_off + 1 behind its
 					// group: sieve its starts first, over everything the next loop asks about
 					const DevSearch &T2 = sm_ds[T.sib_t];
-					const int lo2 = (lo_ & ~31) + T.minglen + T.sib_off;
-					const int hi2 = min((hi_ | 31) + T.maxglen + T.sib_off + 31, Lbytes - 1);
+					const int lo2 = (lo_ & ~31) + T.dlo + 1 + T.sib_off;
+					const int hi2 = min((hi_ | 31) + T.dhi + 1 + T.sib_off + 31, Lbytes - 1);
 					for (int w = (lo2 >> 5) + lane; w <= (hi2 >> 5) && w < nw; w += 32)
-						sv_K2[st * nwb + w] = sieve_word_main(pb, st, T2.dupi, T2.flt, w, T2.minglen - 1, T2.maxglen - 1,
+						sv_K2[st * nwb + w] = sieve_word_main(pb, st, T2.dupi, T2.flt, w, T2.dlo, T2.dhi,
 							[](int, uint32_t f) -> uint32_t { return f; });
 					__syncwarp();
 				}
 				const int k2off = T.sib_off + 1;
 				for (int w = (lo_ >> 5) + lane; w <= (hi_ >> 5) && w < nw; w += 32)
-					sv_K[st * nwb + w] = sieve_word_main(pb, st, T.dupi, T.flt, w, T.minglen - 1, T.maxglen - 1,
+					sv_K[st * nwb + w] = sieve_word_main(pb, st, T.dupi, T.flt, w, T.dlo, T.dhi,
 						[&](int d, uint32_t f) -> uint32_t {
 							// span offset d: the group ends at start + d, its sibling begins k2off later
 							return has_k2 ? f & bits32(K2, min((w << 5) + d + k2off, Lbytes)) : f;
@@ -792,8 +886,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	};
 	// the lane's word of pass `pass` over the tile's helix starts (strand-major)
 	auto sieve_pass = [&](int pass, int &strand_, int &w_) -> uint32_t {
-		const DevSearch &SP = sm_ds[max(c_par.pf_search, 0)]; // (unused by a literal-only sieve)
-		const int pz = c_par.pf_z;
+		const DevSearch &SP = sm_ds[max(A.par.pf_search, 0)]; // (unused by a literal-only sieve)
+		const int pz = A.par.pf_z;
 		const int nv = (int)(gB - gA); // starts of this tile
 		const int it = pass * 32 + lane;
 		uint32_t word = 0;
@@ -815,7 +909,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				// ends asked about at span offset d: e0 + d + m, m = nhl-1-j for length minlen + j
 				const int e0 = (w_ << 5) - SP.minlen - SP.lk_off - (nhl - 1);
 				const bool has_lk = deep && SP.lk_t >= 0;
-				word = !c_par.sv_helix ? ~0u : sieve_word_main(pb, strand_, SP.dupi, SP.flt, w_, SP.minglen - 1, SP.maxglen - 1,
+				word = !A.par.sv_helix ? ~0u : sieve_word_main(pb, strand_, SP.dupi, SP.flt, w_, SP.dlo, SP.dhi,
 					[&](int d, uint32_t f) -> uint32_t {
 						if (!has_lk)
 							return f & (kh[0] | kh[1] | kh[2] | kh[3]);
@@ -829,12 +923,14 @@ __global__ void gm_search_kernel(const ScanArgs A)
 								la |= kh[j] & __funnelshift_r(lo_, hi_, nhl - 1 - j);
 						return f & la;
 					});
+				if (CHAIN)
+					word &= bits32(ch_F0 + strand_ * nwb, max((w_ << 5) - pz, 0));
 				if (LIT) {
 					// literal prefilter as a sieve term: the best literal must begin
 					// lit_lmin..lit_lmax nucleotides after the start (= helix start - pz)
 					const uint32_t *set = sm_lit + strand_ * nwb;
 					uint32_t any = 0;
-					for (int l = c_par.lit_lmin; l <= c_par.lit_lmax; l++)
+					for (int l = A.par.lit_lmin; l <= A.par.lit_lmax; l++)
 						any |= bits32(set, min(max((w_ << 5) - pz + l, 0), Lbytes));
 					word &= any;
 				}
@@ -850,7 +946,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	};
 	// take the lowest survivor out of a sieve word: its start item
 	auto sieve_pop = [&](uint32_t &word, int strand_, int w_) -> int {
-		const int b = (w_ << 5) + __ffs(word) - 1 - c_par.pf_z; // start, in strand buffer coordinates
+		const int b = (w_ << 5) + __ffs(word) - 1 - A.par.pf_z; // start, in strand buffer coordinates
 		word &= word - 1;
 		return strand_ ? TILE + (Lbytes - 1 - b - H) : b - H;
 	};
@@ -892,6 +988,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				break;
 			load_tile(0, t);
 			if (SIEVE) {
+				if (CHAIN)
+					chain_build();
 				if (deep)
 					sieve_aux();
 				for (int pass_ = 0; pass_ < sv_npass; pass_++) {
@@ -956,6 +1054,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 						load_tile(nb, t);
 						sv_pass = 0;
 						sw = 0;
+						if (CHAIN)
+							chain_build();
 						if (deep)
 							sieve_aux();
 						continue;
@@ -1058,44 +1158,38 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	const int tid = threadIdx.x, nt = blockDim.x;
 	const int lane = tid & 31;
-	const int NS = c_par.n_searches, ND = c_par.n_descr;
-	const int W = c_par.w_winsize;
-	const int Lc = c_par.halo - W;            // context nucleotides kept on each side
-	const int wstride = c_par.win_stride;     // bytes per lane window (odd number of words)
+	const int NS = A.par.n_searches, ND = A.par.n_descr;
+	const int W = A.par.w_winsize;
+	const int Lc = A.par.halo - W;            // context nucleotides kept on each side
+	const int wstride = A.par.win_stride;     // bytes per lane window (odd number of words)
 	const int Wtot = W + 2 * Lc;
 
-	uint8_t *p = smem_raw;
-	DevSearch *sm_ds = reinterpret_cast<DevSearch *>(p);       p += ((NS * sizeof(DevSearch) + 15) & ~15);
-	gm_pairset_t *sm_ps = reinterpret_cast<gm_pairset_t *>(p); p += ((c_plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~15);
-	uint32_t *sm_elmm = reinterpret_cast<uint32_t *>(p);       p += ((ND * 4 + 15) & ~15);
+	StagedPlan sp;
+	uint8_t *p = stage_plan(smem_raw, A, tid, nt, sp);
+	DevSearch *sm_ds = sp.ds;
+	uint32_t *sm_elmm = sp.elmm;
 	uint8_t *sm_win = p;                                       p += (size_t)nt * wstride;
-	uint32_t *sm_bits = reinterpret_cast<uint32_t *>(p);       p += (size_t)nt * c_par.win_bits * 4;
+	uint32_t *sm_bits = reinterpret_cast<uint32_t *>(p);       p += (size_t)nt * A.par.win_bits * 4;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
 
-	for (int i = tid; i < NS * (int)(sizeof(DevSearch) / 4); i += nt)
-		reinterpret_cast<uint32_t *>(sm_ds)[i] = reinterpret_cast<const uint32_t *>(c_ds)[i];
-	for (int i = tid; i < c_plan.n_pairsets * (int)(sizeof(gm_pairset_t) / 4); i += nt)
-		reinterpret_cast<uint32_t *>(sm_ps)[i] = reinterpret_cast<const uint32_t *>(c_plan.pairsets)[i];
-	for (int i = tid; i < ND; i += nt)
-		sm_elmm[i] = pk16(c_plan.elems[i].minlen, c_plan.elems[i].maxlen);
-
 	Lane L;
+	L.P = sp.pv;
 	L.st = sm_state + tid;
 	L.nt = nt;
 	L.ds = sm_ds;
-	L.ps = sm_ps;
+	L.ps = sp.ps;
 	L.NS = NS;
 	L.ND = ND;
-	L.el_base = NS + c_par.frame_words;
+	L.el_base = NS + A.par.frame_words;
 	uint8_t *mywin = sm_win + (size_t)tid * wstride;
 	L.sq = mywin + Lc;
 	// the lane's own pair bitsets over its window (same layout as a tile's, one
 	// strand; the lane stride is an odd number of words, so the lanes of a warp
 	// hit different banks): bit Lc + rel <-> window-relative position rel
 	PairBits mypb;
-	mypb.base = sm_bits + (size_t)tid * c_par.win_bits;
+	mypb.base = sm_bits + (size_t)tid * A.par.win_bits;
 	mypb.nwb = ((Wtot + 31) >> 5) + 3;
-	mypb.n_dups = c_par.n_dups;
+	mypb.n_dups = A.par.n_dups;
 	L.szero = L.slen = L.comp = 0;
 	L.rec = 0;
 	L.seq = 0;
@@ -1115,7 +1209,7 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	// one after the other while the rest of the GPU idles
 	const unsigned long long n_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
 	const int per = (int)max(1ull, min(32ull, (wl_n + n_warps - 1) / n_warps));
-	const int rmin = min(c_par.refill_min, per);
+	const int rmin = min(A.par.refill_min, per);
 	const unsigned long long gwarp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
 	int taken = 0;
 
@@ -1184,7 +1278,7 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 					mb[3 * nwl + w] = b3;
 					// the other tables: unions of the base bitsets
 					for (int dd = 1; dd < mypb.n_dups; dd++) {
-						const unsigned dup = c_par.dups[dd];
+						const unsigned dup = A.par.dups[dd];
 #pragma unroll
 						for (int x = 0; x < 4; x++) {
 							const unsigned row = dup >> (x * 5);

@@ -19,6 +19,7 @@
 // [word][thread] (bank = thread: conflict-free for any mix of depths).
 #pragma once
 
+#include <stddef.h>
 #include <stdint.h>
 #include "gpumotif_plan.h"
 
@@ -49,22 +50,38 @@ struct DevSearch {
 	int fr;                // word offset of this search's frame in the lane state
 	int dupi;              // index of `duplex` in DevParams::dups (pair bitsets), or -1
 	int flt;               // span-end prefilter: req | budget << 8 | first_must << 16
-	// look-ahead pruning: the next helix head reachable through fixed-length single
-	// strands, as first interior element (kid) and as following sibling (sib), with
-	// the nucleotides in between; -1 if there is none
+	// look-ahead pruning, in DESCRIPTOR order (elements are contiguous on the sequence):
+	// the next helix head reachable through fixed-length single strands from the end of
+	// this helix's 5' strand (kid) and from the end of its 3' strand (sib), with the
+	// nucleotides in between; -1 if there is none or it is searched earlier
 	int kid_t, kid_off;
 	int sib_t, sib_off;
-	// tail look-ahead: the LAST helix group of this helix's interior chain (only
-	// fixed-length single strands behind it): it must end lk_off nucleotides before
-	// the interior does, so its 3' end is known as soon as this helix is chosen
+	// tail look-ahead: the helix whose 3' strand ends lk_off nucleotides (fixed-length
+	// single strands) before this helix's 3' strand begins: its 3' end is known as
+	// soon as this helix is chosen
 	int lk_t, lk_off;
+	// Span offsets s3 - s5 the helix can take at all: [minglen - 1, maxglen - 1] for a
+	// proper helix or quadruplex (what find_motif's span loop visits); for a pseudoknot
+	// helix the static bounds from the lengths of the elements between its strands.
+	int dlo, dhi;
+	int nest;               // bit 0: kid_t lies inside this helix (its span ends before s3 - hl)
+	// Probes: single strands of fixed length with seq= whose place is known as soon as
+	// this helix is chosen (only fixed-length single strands between them and one of
+	// the helix's boundaries) and which are searched later: if one cannot match there,
+	// the subtree cannot reach the hit sink.
+	// packed: anchor (2 bits: 0 after the 5' strand, 1 after the 3' strand, 2 before the
+	// 3' strand) | off << 2 (10 bits) | len << 12 (8) | regex << 20 (5) | mismatch << 25 (4)
+	int n_probe;
+	unsigned probe[4];
 };
-static_assert(sizeof(DevSearch) == 31 * 4, "DevSearch is staged with an odd word stride");
+static_assert(sizeof(DevSearch) == 39 * 4, "DevSearch is staged with an odd word stride");
 
 #define GM_MAX_DUPS 8
+#define GM_MAX_CHAIN 40
 
 struct DevParams {
 	int n_searches, n_descr;
+	int n_pairsets, n_regex, n_scopes, n_lentab, n_sites; // used prefixes of the plan's tables
 	int w_winsize;          // min(rm_dmaxlen, windowsize), src/find_motif.c:179
 	int dminlen;
 	int strict_helices;
@@ -84,6 +101,13 @@ struct DevParams {
 	int pf_deep;            // second stage behind the sieve: kid / tail look-ahead per span end
 	int sv_helix;           // the sieve has a helix term (pf_search); otherwise only the literal term
 	int sv_id;              // index in dups[] of the identity table (its bitsets are the base bitsets)
+	// Composition chain (a term of the level-0 sieve, chain_build in gm_machine.cuh): the
+	// descriptor's elements from last to first as steps (min, max, allowed bases,
+	// exception budget per length); a start survives only if every element can be laid
+	// out contiguously behind it with its strand made of bases that can pair at all.
+	int chain;              // number of steps, 0 = off
+	unsigned chain_w0[GM_MAX_CHAIN]; // min (12 bits) | max << 12 (12) | allowed bases << 24 (4) | both ends << 28 | constrained << 29
+	unsigned chain_w1[GM_MAX_CHAIN]; // budget of length min + i in bits 2i, 2i+1 (3 = no limit)
 	int lit_present;        // literal prefilter (gm_plan_t::literal): regex index, window, length
 	int lit_rx, lit_lmin, lit_lmax, lit_mm, lit_len;
 	int lite;               // plan of single strands and proper helices only: the lane
@@ -97,7 +121,7 @@ struct DevParams {
 #define GM_FW_SS 2
 #define GM_FW_HX 7
 #define GM_FW_QU 9
-#define GM_FW_PK 16 // 9..15: find_minlen/find_maxlen results, constant while the level is active
+#define GM_FW_PK 18 // 9..15: find_minlen/find_maxlen results, constant while the level is active; 16,17: candidate mask of the level
 
 __device__ __forceinline__ uint32_t pk16(int a, int b)
 {
@@ -116,8 +140,33 @@ __device__ __forceinline__ int paired(unsigned duplex, int v5, int v3)
 	return (duplex >> (bcode_of(v5) * 5 + bcode_of(v3))) & 1u;
 }
 
+// The plan as the kernels see it: every table a kernel reads with a per-lane index is
+// staged into SHARED memory at kernel start (stage_plan, gm_kernel.cuh) from the
+// context's own device copy of the plan.  (It used to live in __constant__ memory:
+// one symbol per device, shared by every context on it, and a divergent index into
+// constant memory is replayed once per distinct address.)
+struct DevRegex {           // the part of gm_regex_t the device reads (its first 176 bytes)
+	int32_t n_items, bol, eol, npos, closure_iters, mm_len;
+	uint64_t skip, star, dot;
+	uint64_t B[16];
+};
+static_assert(sizeof(DevRegex) == offsetof(gm_regex_t, items), "DevRegex mirrors the head of gm_regex_t");
+
+struct PlanView {
+	DevParams par;
+	const gm_elem_t *elems;
+	const gm_pairset_t *pairsets;
+	const DevRegex *regex;
+	const int32_t *scopes;
+	const uint8_t *lentab;
+	const gm_site_t *sites;
+	gm_ctxel_t lctx, rctx;
+	int n_sites, n_pairsets, n_regex, pad_;
+};
+
 struct Lane {
 	// views into shared memory
+	const PlanView *P;       // the staged plan
 	uint32_t *st;            // this thread's column of the state array
 	int nt;                  // threads per block (row stride)
 	const uint8_t *sq;       // sq[rel] = tile byte at window-relative position
@@ -169,7 +218,7 @@ __device__ __forceinline__ void set_mpr(Lane &L, int d, int mpr)
 // Boolean result only: for the operator subset the plan admits (classes, '.',
 // '*', \{m,n\}, '^', '$') "some backtracking path succeeds" is regular-language
 // membership, which the position automaton decides exactly.
-__device__ __noinline__ int rx_match(const gm_regex_t &rx, const uint8_t *s, int n)
+__device__ __noinline__ int rx_match(const DevRegex &rx, const uint8_t *s, int n)
 {
 	const uint64_t skip = rx.skip, star = rx.star;
 	const uint64_t accept = (uint64_t)1 << rx.npos;
@@ -203,7 +252,7 @@ __device__ __noinline__ int rx_match(const gm_regex_t &rx, const uint8_t *s, int
 // Returns 1 and the mismatch count of the first (leftmost) placement that
 // stays within l_mm; on failure *n_mm is what the last placement tried left
 // behind (mm_advance counts into the caller's s_n_mismatches as it goes).
-__device__ __noinline__ int rx_match_mm(const gm_regex_t &rx, const uint8_t *s, int n, int l_mm, int *n_mm)
+__device__ __noinline__ int rx_match_mm(const DevRegex &rx, const uint8_t *s, int n, int l_mm, int *n_mm)
 {
 	const int m = rx.mm_len;
 	const int last = rx.bol ? 0 : n;

@@ -27,7 +27,6 @@ using namespace gm;
 
 static thread_local char g_err[512] = "";
 struct gm_ctx;
-static gm_ctx *g_const_owner[64];
 
 static int fail(const char *fmt, ...)
 {
@@ -60,6 +59,10 @@ struct gm_ctx {
 	std::vector<int64_t> chunk_end;  // nucleotide offsets where the chunks end
 	bool upload_fresh;               // no scan has consumed the last upload yet
 	cudaEvent_t up_ev[2];            // upload start / end on copy_stream
+	// this context's device copy of the plan and of the per-search table (the kernels
+	// stage what they use into shared memory; nothing is shared between contexts)
+	gm_plan_t *d_plan;
+	DevSearch *d_ds;
 	// database
 	uint8_t *d_chars;      // staging for uploaded characters
 	size_t chars_cap;
@@ -335,6 +338,11 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	memset(par, 0, sizeof *par);
 	par->n_searches = NS;
 	par->n_descr = ND;
+	par->n_pairsets = pl->n_pairsets;
+	par->n_regex = pl->n_regex;
+	par->n_scopes = pl->n_scopes;
+	par->n_lentab = pl->n_lentab;
+	par->n_sites = pl->n_sites;
 	par->w_winsize = W;
 	par->dminlen = pl->dminlen;
 	par->strict_helices = pl->strict_helices;
@@ -383,12 +391,33 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		}
 	}
 	par->frame_words = fr;
+	// span offsets each helix can take (DevSearch::dlo / dhi)
+	for (int s = 0; s < NS; s++) {
+		DevSearch &S = ds[s];
+		S.dlo = S.dhi = 0;
+		if (S.kind == K_WC || S.kind == K_QU) {
+			S.dlo = S.minglen - 1;
+			S.dhi = S.maxglen - 1;
+		}
+		if (S.kind == K_PK || ((S.kind == K_WC || S.kind == K_QU) && !S.loop)) {
+			// find_minlen / find_maxlen over everything between the strands
+			// (src/find_motif.c:642-665) with nothing matched yet
+			long lo = 2L * S.minlen, hi = 2L * S.maxlen;
+			for (int k = S.d + 1; k < S.d3; k++) {
+				lo += pl->elems[k].minlen;
+				hi += pl->elems[k].maxlen;
+			}
+			S.dlo = (int)std::min<long>(lo - 1, 32000);
+			S.dhi = (int)std::min<long>(hi - 1, 32000);
+		}
+		S.dhi = std::min(S.dhi, W - 1);
+	}
 	// bitsets of the transposed tables, for masks that run from a known 3' end
 	// (wc_mask_rev); wc/gu tables are symmetric and share their own bitsets
 	for (int s = 0; s < NS; s++) {
 		DevSearch &S = ds[s];
 		S.dupi_t = -1;
-		if (S.kind != K_WC || S.dupi < 0)
+		if ((S.kind != K_WC && S.kind != K_PK && S.kind != K_QU) || S.dupi < 0)
 			continue;
 		unsigned t = 0;
 		for (int x = 0; x < 5; x++)
@@ -404,47 +433,82 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		if (k < par->n_dups)
 			S.dupi_t = k;
 	}
-	// look-ahead targets (see DevSearch::kid_t / sib_t / lk_t)
+	// Look-ahead targets and probes (see DevSearch).  Elements are contiguous on the
+	// sequence in descriptor order, so whatever is separated from one of this helix's
+	// strand boundaries by fixed-length single strands only has a known place as soon
+	// as the helix is chosen -- whether the search order gets there next or much later.
 	const bool no_tail = getenv("GPUMOTIF_NO_TAIL") != NULL;
+	const bool no_look = getenv("GPUMOTIF_NO_LOOK") != NULL;
+	const bool no_probe = getenv("GPUMOTIF_NO_PROBE") != NULL;
+	auto fixed_ss = [&](int k) {
+		return k >= 0 && k < ND && pl->elems[k].type == GM_SS && pl->elems[k].minlen == pl->elems[k].maxlen;
+	};
+	// search of the helix whose 5' strand is element k, if its candidate masks are usable
+	auto head_of = [&](int k) -> int {
+		if (k < 0 || k >= ND)
+			return -1;
+		const gm_elem_t &e = pl->elems[k];
+		if (e.type != GM_H5 && e.type != GM_Q1)
+			return -1;
+		const int t = e.searchno;
+		if (t < 0 || t >= NS || ds[t].d != k || ds[t].dupi < 0 || (ds[t].flt & 0xff) == 0)
+			return -1;
+		return t;
+	};
 	for (int s = 0; s < NS; s++) {
 		DevSearch &S = ds[s];
 		S.kid_t = S.sib_t = S.lk_t = -1;
 		S.kid_off = S.sib_off = S.lk_off = 0;
-		if (S.kind != K_WC)
+		S.nest = 0;
+		S.n_probe = 0;
+		S.probe[0] = S.probe[1] = S.probe[2] = S.probe[3] = 0;
+		if (S.kind != K_WC && S.kind != K_PK && S.kind != K_QU)
 			continue;
-		{
-			// the interior chain s+1 -> next_s -> ...: its last helix group, if only
-			// fixed-length single strands follow it
-			int chain[GM_MAX_DESCR], n = 0;
-			for (int u = s + 1; u >= 0 && u < NS && n < GM_MAX_DESCR; u = ds[u].next_s)
-				chain[n++] = u;
-			int off = 0, k = n - 1;
-			while (k >= 0 && ds[chain[k]].kind == K_SS && ds[chain[k]].minlen == ds[chain[k]].maxlen) {
-				off += ds[chain[k]].minlen;
-				k--;
+		auto add_probe = [&](int anchor, int off, int k) {
+			const gm_elem_t &e = pl->elems[k];
+			if (no_probe || e.regex < 0 || e.searchno <= s || S.n_probe >= 4 || off > 1023 || e.minlen > 255 ||
+			    e.regex > 31 || e.mismatch > 15 || e.minlen == 0)
+				return;
+			S.probe[S.n_probe++] = (unsigned)anchor | ((unsigned)off << 2) | ((unsigned)e.minlen << 12) |
+				((unsigned)e.regex << 20) | ((unsigned)e.mismatch << 25);
+		};
+		// forward from the end of the 5' strand (which = 0) and of the 3' strand (1)
+		for (int which = 0; which < 2; which++) {
+			int k = (which == 0 ? S.d : S.d3) + 1, off = 0;
+			while (fixed_ss(k)) {
+				add_probe(which, off, k);
+				off += pl->elems[k].minlen;
+				k++;
 			}
-			if (k >= 0 && !no_tail) {
-				const DevSearch &T = ds[chain[k]];
-				if (T.kind == K_WC && T.dupi_t >= 0 && (T.flt & 0xff) > 0) {
-					S.lk_t = chain[k];
-					S.lk_off = off;
+			const int t = head_of(k);
+			if (t > s && !no_look) {
+				if (which == 0) {
+					S.kid_t = t;
+					S.kid_off = off;
+					if (ds[t].d3 < S.d3)
+						S.nest |= 1;
+				} else {
+					S.sib_t = t;
+					S.sib_off = off;
 				}
 			}
 		}
-		for (int which = 0; which < 2; which++) {
-			int u = which == 0 ? s + 1 : S.next_s, off = 0;
-			while (u >= 0 && u < NS && ds[u].kind == K_SS && ds[u].minlen == ds[u].maxlen &&
-			       ds[u].rx5 < 0 && ds[u].next_s == u + 1) {
-				off += ds[u].minlen;
-				u++;
+		// backward from the start of the 3' strand
+		{
+			int k = S.d3 - 1, off = 0;
+			while (k > S.d && fixed_ss(k)) {
+				off += pl->elems[k].minlen;
+				add_probe(2, off - pl->elems[k].minlen, k);
+				k--;
 			}
-			if (u >= 0 && u < NS && ds[u].kind == K_WC && ds[u].dupi >= 0 && (ds[u].flt & 0xff) > 0) {
-				if (which == 0) {
-					S.kid_t = u;
-					S.kid_off = off;
-				} else {
-					S.sib_t = u;
-					S.sib_off = off;
+			if (k > S.d && !no_tail && !no_look) {
+				const gm_elem_t &e = pl->elems[k];
+				if ((e.type == GM_H3 || e.type == GM_Q4) && e.n_mates >= 1) {
+					const int t = head_of(e.mates[0]);
+					if (t > s && ds[t].d3 == k && ds[t].dupi_t >= 0) {
+						S.lk_t = t;
+						S.lk_off = off;
+					}
 				}
 			}
 		}
@@ -491,8 +555,7 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	if (par->pf_search >= 0 && getenv("GPUMOTIF_NO_SIEVE") == NULL) {
 		const DevSearch &SP = ds[par->pf_search];
 		const int req = SP.flt & 0xff, budget = (SP.flt >> 8) & 0xff;
-		if ((SP.kind == K_WC || SP.kind == K_QU) && req >= 1 && budget <= 1 &&
-		    SP.minglen - 1 - 2 * (req - 1) >= 1 && SP.maxglen - SP.minglen <= 160) {
+		if (req >= 1 && budget <= 1 && SP.dlo - 2 * (req - 1) >= 1 && SP.dhi - SP.dlo <= 160 && SP.dhi >= SP.dlo) {
 			par->sieve = 1;
 			par->sv_helix = 1;
 			par->sv_id = 0;
@@ -500,9 +563,9 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 			// sievable: a budget of at most one) and few lengths to try
 			auto sievable = [&](int t) {
 				return t >= 0 && (ds[t].flt & 0xff) >= 1 && ((ds[t].flt >> 8) & 0xff) <= 1 &&
-					ds[t].minglen - 1 - 2 * ((ds[t].flt & 0xff) - 1) >= 1;
+					ds[t].dlo - 2 * ((ds[t].flt & 0xff) - 1) >= 1 && ds[t].dhi >= ds[t].dlo;
 			};
-			if (SP.kind == K_WC && SP.minlen >= 1 && SP.maxlen - SP.minlen <= 3 &&
+			if ((SP.kind == K_WC || SP.kind == K_PK) && SP.minlen >= 1 && SP.maxlen - SP.minlen <= 3 &&
 			    (SP.lk_t < 0 || sievable(SP.lk_t)) && (SP.kid_t < 0 || sievable(SP.kid_t)) &&
 			    (SP.lk_t >= 0 || SP.kid_t >= 0) && getenv("GPUMOTIF_NO_DEEP") == NULL)
 				par->pf_deep = 1;
@@ -515,6 +578,112 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	// a literal alone also makes a sieve (its occurrence bitset, ORed over the window)
 	if (!par->sieve && par->lit_present && par->lit_lmax - par->lit_lmin <= 256 && getenv("GPUMOTIF_NO_SIEVE") == NULL)
 		par->sieve = 1;
+	// Composition chain.  Projection of every pair table onto its strands: a base
+	// that pairs with nothing at a strand can only sit there as a mispair.
+	par->chain = 0;
+	if (getenv("GPUMOTIF_NO_CHAIN") == NULL && getenv("GPUMOTIF_NO_SIEVE") == NULL) {
+		struct Step { int mn, mx, cm, both, con; unsigned bud; };
+		std::vector<Step> steps;
+		bool any_con = false;
+		for (int d = ND - 1; d >= 0; d--) {
+			const gm_elem_t &e = pl->elems[d];
+			Step st = {e.minlen, e.maxlen, 15, 0, 0, 0};
+			if (e.type != GM_SS && e.pairset >= 0) {
+				// head of the group and this strand's index in it
+				const int head = (e.type == GM_H5 || e.type == GM_P5 || e.type == GM_T1 || e.type == GM_Q1) ? d : e.mates[0];
+				const gm_elem_t &eh = pl->elems[head];
+				const int nst = 1 + eh.n_mates;
+				int k = 0;
+				if (head != d)
+					for (int j = 0; j < eh.n_mates; j++)
+						if (eh.mates[j] == d)
+							k = j + 1;
+				const gm_pairset_t &ps = pl->pairsets[eh.pairset];
+				int cm = 0;
+				if (nst == 2) {
+					for (int x = 0; x < 4; x++)
+						for (int y = 0; y < 4; y++)
+							if ((ps.duplex >> (x * 5 + y)) & 1u)
+								cm |= 1 << (k == 0 ? x : y);
+				} else {
+					const int nn = nst == 3 ? 125 : 625;
+					for (int i = 0; i < nn; i++) {
+						if (!((ps.multi[i >> 5] >> (i & 31)) & 1u))
+							continue;
+						int digs[4], v = i;
+						for (int j = nst - 1; j >= 0; j--) {
+							digs[j] = v % 5;
+							v /= 5;
+						}
+						bool acgt = true;
+						for (int j = 0; j < nst; j++)
+							if (digs[j] > 3)
+								acgt = false;
+						if (acgt)
+							cm |= 1 << digs[k];
+						else
+							cm = 15; // a table in which n pairs: no constraint
+					}
+				}
+				// exception budget by length: the mispair budget of the matcher that decides
+				// this group, one more where an unpaired outermost position is not counted
+				// (src/find_motif.c:1014-1017,1247-1260)
+				const int lens = e.maxlen - e.minlen + 1;
+				if (cm != 15 && lens >= 1 && lens <= 8 && e.minlen >= 1 && e.maxlen <= 255) {
+					const gm_elem_t &eb = nst == 4 ? pl->elems[eh.mates[0]] : eh; // quadruplex parameters come from q2
+					const bool p5 = (eb.ends & GM_5PAIRED) != 0, p3 = (eb.ends & GM_3PAIRED) != 0;
+					unsigned bud = 0;
+					bool ok = true;
+					for (int i = 0; i < lens; i++) {
+						const int hl = e.minlen + i;
+						int b = nst == 2 ? eh.mplim : (eb.mptab >= 0 ? pl->lentab[eb.mptab + hl] : 255);
+						if (nst == 3)
+							b = std::max(b, (int)eh.mplim); // t1/t3 are placed by match_phlx with its own budget first
+						if (!p5)
+							b++;
+						if (b < 0)
+							ok = false;
+						bud |= (unsigned)std::min(b, 3) << (2 * i);
+					}
+					if (ok) {
+						st.cm = cm;
+						st.both = p5 && p3;
+						st.con = 1;
+						st.bud = bud;
+						any_con = true;
+					}
+				}
+			}
+			if (!st.con && !steps.empty() && !steps.back().con) {
+				// consecutive unconstrained elements: one dilation
+				steps.back().mn += st.mn;
+				steps.back().mx = (int)std::min<long>((long)steps.back().mx + st.mx, 4095);
+			} else
+				steps.push_back(st);
+			if (steps.back().mx > 4095)
+				steps.back().mx = 4095;
+		}
+		bool fits = any_con && (int)steps.size() <= GM_MAX_CHAIN;
+		long span = 0;
+		for (const Step &st : steps) {
+			if (st.mn > 4095)
+				fits = false;
+			span += st.mx - st.mn;
+		}
+		if (span > 4096)
+			fits = false; // too many shifted words per start word to be worth it
+		if (fits) {
+			par->chain = (int)steps.size();
+			for (size_t i = 0; i < steps.size(); i++) {
+				const Step &st = steps[i];
+				par->chain_w0[i] = (unsigned)st.mn | ((unsigned)st.mx << 12) | ((unsigned)st.cm << 24) |
+					((unsigned)st.both << 28) | ((unsigned)st.con << 29);
+				par->chain_w1[i] = st.bud;
+			}
+			if (!par->sieve)
+				par->sieve = 1; // the chain alone makes a sieve
+		}
+	}
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
 		if ((ds[s].kind != K_SS && ds[s].kind != K_WC) || ds[s].hmm)
@@ -547,6 +716,49 @@ extern "C" int gm_plan_check(const gm_plan_t *plan)
 	return check_plan(plan, ds, &par);
 }
 
+extern "C" int gm_plan_describe(const gm_plan_t *plan, char *out, size_t cap)
+{
+	static thread_local DevSearch ds[GM_MAX_DESCR];
+	DevParams par;
+	if (out == NULL || cap == 0)
+		return fail("bad argument");
+	out[0] = 0;
+	if (check_plan(plan, ds, &par))
+		return -1;
+	size_t n = 0;
+	auto put = [&](const char *fmt, ...) {
+		if (n + 1 >= cap)
+			return;
+		va_list ap;
+		va_start(ap, fmt);
+		int k = vsnprintf(out + n, cap - n, fmt, ap);
+		va_end(ap);
+		if (k > 0)
+			n = std::min(cap - 1, n + (size_t)k);
+	};
+	static const char *kn[] = {"ss", "wc", "pk", "ph", "tr", "qu"};
+	put("window %d halo %d lite %d n_dups %d refill %d\n", par.w_winsize, par.halo, par.lite, par.n_dups, par.refill_min);
+	put("level0: pf_search %d pf_z %d sieve %d helix-term %d deep %d literal %d (len %d at %d..%d mm %d) chain %d\n", par.pf_search,
+	    par.pf_z, par.sieve, par.sv_helix, par.pf_deep, par.lit_present, par.lit_len, par.lit_lmin, par.lit_lmax, par.lit_mm,
+	    par.chain);
+	for (int s = 0; s < par.n_searches; s++) {
+		const DevSearch &S = ds[s];
+		put("search %2d %s d %d d3 %d loop %d next %d len %d..%d D %d..%d req %d budget %d first %d dup %d/%d", s, kn[S.kind], S.d, S.d3,
+		    S.loop, S.next_s, S.minlen, S.maxlen, S.dlo, S.dhi, S.flt & 0xff, (S.flt >> 8) & 0xff, (S.flt >> 16) & 1, S.dupi, S.dupi_t);
+		if (S.kid_t >= 0)
+			put(" kid %d+%d%s", S.kid_t, S.kid_off, (S.nest & 1) ? "" : " (not nested)");
+		if (S.sib_t >= 0)
+			put(" sib %d+%d", S.sib_t, S.sib_off);
+		if (S.lk_t >= 0)
+			put(" tail %d-%d", S.lk_t, S.lk_off);
+		for (int i = 0; i < S.n_probe; i++)
+			put(" probe(%s off %u len %u rx %u mm %u)", (S.probe[i] & 3) == 0 ? "after-5'" : (S.probe[i] & 3) == 1 ? "after-3'" : "before-3'",
+			    (S.probe[i] >> 2) & 1023, (S.probe[i] >> 12) & 255, (S.probe[i] >> 20) & 31, (S.probe[i] >> 25) & 15);
+		put("\n");
+	}
+	return 0;
+}
+
 // -------------------------------------------------------------- context
 
 static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state = true)
@@ -558,11 +770,9 @@ static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state 
 	const size_t lit = c->par.lit_present ? (((size_t)2 * (((Lb + 31) >> 5) + 4) * 4) + 15) & ~(size_t)15 : 0;
 	const size_t buf_bytes = 2 * (size_t)Lb + pb + (GM_REC_CACHE + 2) * 8 + lit;
 	const size_t warp_bytes = 16 + stage + (with_state ? 2 : 1) * buf_bytes + GM_QCAP * 2 +
-		(c->par.sieve ? ((6 * (size_t)(((Lb + 31) >> 5) + 4) * 4 + 15) & ~(size_t)15) : 0);
-	size_t n = 0;
-	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
-	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
-	n += (c->par.n_descr * 4 + 15) & ~15;
+		(c->par.sieve ? ((6 * (size_t)(((Lb + 31) >> 5) + 4) * 4 + 15) & ~(size_t)15) : 0) +
+		(c->par.chain ? ((6 * (size_t)(((Lb + 31) >> 5) + 4) * 4 + 15) & ~(size_t)15) : 0);
+	size_t n = plan_smem_bytes(c->par);
 	n += c->par.lit_present ? 16 * 8 : 0;
 	n += (size_t)(threads >> 5) * warp_bytes;
 	if (with_state)
@@ -572,10 +782,7 @@ static size_t smem_need(const gm_ctx *c, int threads, int tile, bool with_state 
 
 static size_t dfs_smem_need(const gm_ctx *c, int threads)
 {
-	size_t n = 0;
-	n += (c->par.n_searches * sizeof(DevSearch) + 15) & ~(size_t)15;
-	n += (c->plan.n_pairsets * sizeof(gm_pairset_t) + 15) & ~(size_t)15;
-	n += (c->par.n_descr * 4 + 15) & ~15;
+	size_t n = plan_smem_bytes(c->par);
 	n += (size_t)threads * c->par.win_stride;
 	n += (size_t)threads * c->par.win_bits * 4;
 	n += (size_t)c->par.words_per_lane * threads * 4;
@@ -732,10 +939,7 @@ static int configure_launch(gm_ctx *c, int tile)
 	if (getenv("GPUMOTIF_DEBUG") != NULL && c->use_split)
 		fprintf(stderr, "gpumotif: split path, tile %d, sieve/prefilter %d x %d (%zu B), dfs %d x %d (%zu B)\n", c->par.tile,
 			c->a_blocks, c->a_threads, c->a_smem, c->b_blocks, c->b_threads, c->b_smem);
-	CU(cudaMemcpyToSymbolAsync(c_par, &c->par, sizeof c->par, 0, cudaMemcpyHostToDevice, c->stream));
-	if (c->device < 64 && g_const_owner[c->device] != c)
-		g_const_owner[c->device] = NULL; // force a full re-bind of the __constant__ plan at the next launch
-	return 0;
+	return 0; // the parameters travel with every launch (ScanArgs::par)
 }
 
 extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
@@ -746,6 +950,8 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	gm_ctx *c = new gm_ctx();
 	memset(&c->stats, 0, sizeof c->stats);
 	c->d_chars = c->d_packed = NULL;
+	c->d_plan = NULL;
+	c->d_ds = NULL;
 	c->d_text = NULL;
 	c->d_hdr_off = NULL;
 	c->d_fsum = c->d_fstart = NULL;
@@ -823,9 +1029,13 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 		gm_ctx_destroy(c);
 		return fail("cudaMalloc(counters) failed");
 	}
-	cudaMemcpyToSymbolAsync(c_plan, &c->plan, sizeof c->plan, 0, cudaMemcpyHostToDevice, c->stream);
-	cudaMemcpyToSymbolAsync(c_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, 0, cudaMemcpyHostToDevice, c->stream);
-	g_const_owner[device < 64 ? device : 63] = device < 64 ? c : NULL;
+	if (cudaMalloc(&c->d_plan, sizeof(gm_plan_t)) != cudaSuccess ||
+	    cudaMalloc(&c->d_ds, sizeof(DevSearch) * GM_MAX_DESCR) != cudaSuccess ||
+	    cudaMemcpyAsync(c->d_plan, &c->plan, sizeof c->plan, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+	    cudaMemcpyAsync(c->d_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+		gm_ctx_destroy(c);
+		return fail("plan upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+	}
 	if (configure_launch(c, 0)) {
 		gm_ctx_destroy(c);
 		return -1;
@@ -843,8 +1053,6 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 	if (c == NULL)
 		return;
 	cudaSetDevice(c->device);
-	if (c->device >= 0 && c->device < 64 && g_const_owner[c->device] == c)
-		g_const_owner[c->device] = NULL;
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	if (c->copy_stream)
@@ -858,6 +1066,8 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 			cudaEventDestroy(c->up_ev[i]);
 	if (c->copy_stream)
 		cudaStreamDestroy(c->copy_stream);
+	cudaFree(c->d_plan);
+	cudaFree(c->d_ds);
 	cudaFree(c->d_chars);
 	cudaFree(c->d_text);
 	cudaFree(c->d_hdr_off);
@@ -887,6 +1097,8 @@ extern "C" int gm_set_hit_capacity(gm_ctx *c, size_t n)
 {
 	if (c == NULL || n == 0)
 		return fail("bad argument");
+	if (c->pending)
+		return fail("a scan is in flight");
 	c->hit_cap = n;
 	cudaSetDevice(c->device);
 	cudaFree(c->d_hits);
@@ -898,6 +1110,8 @@ extern "C" int gm_set_tile(gm_ctx *c, int tile)
 {
 	if (c == NULL || (tile != 0 && (tile < 32 || tile > 32768)))
 		return fail("tile must be 0 (automatic) or in [32, 32768]");
+	if (c->pending)
+		return fail("a scan is in flight");
 	CU(cudaSetDevice(c->device));
 	return configure_launch(c, tile);
 }
@@ -1135,30 +1349,16 @@ extern "C" int64_t gm_db_total_nt(const gm_ctx *c) { return c ? c->total_nt : -1
 
 // ------------------------------------------------------------------ scan
 
-// __constant__ symbols are per device, not per context: remember whose plan is
-// resident and re-upload when another context of this process scans.
-
-static int bind_plan(gm_ctx *c)
-{
-	if (c->device < 64 && g_const_owner[c->device] == c)
-		return 0;
-	CU(cudaMemcpyToSymbolAsync(c_plan, &c->plan, sizeof c->plan, 0, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyToSymbolAsync(c_ds, c->ds, sizeof(DevSearch) * GM_MAX_DESCR, 0, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyToSymbolAsync(c_par, &c->par, sizeof c->par, 0, cudaMemcpyHostToDevice, c->stream));
-	if (c->device < 64)
-		g_const_owner[c->device] = c;
-	return 0;
-}
-
 static int launch(gm_ctx *c)
 {
-	if (bind_plan(c))
-		return -1;
 	if (c->d_hits == NULL) {
 		CU(cudaMalloc(&c->d_hits, c->hit_cap * (size_t)c->stride_words * 4));
 	}
 	CU(cudaMemsetAsync(c->d_counters, 0, 32 * sizeof(unsigned long long), c->stream));
 	ScanArgs A;
+	A.par = c->par;
+	A.plan = c->d_plan;
+	A.ds = c->d_ds;
 	A.packed = c->d_packed;
 	A.total_nt = c->total_nt;
 	A.rec_off = c->d_rec_off;

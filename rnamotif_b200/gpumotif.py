@@ -35,7 +35,7 @@ class GpuMotifError(RuntimeError):
 _lib = None
 
 EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_ctx_create", "gm_ctx_destroy",
-           "gm_plan_check", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
+           "gm_plan_check", "gm_plan_describe", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
            "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
            "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits", "gm_order_hits"]
@@ -54,6 +54,7 @@ def lib():
         L.gm_ctx_destroy.argtypes = [C.c_void_p]
         L.gm_ctx_destroy.restype = None
         L.gm_plan_check.argtypes = [C.c_char_p]
+        L.gm_plan_describe.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
         L.gm_db_upload_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gm_db_set_device_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gm_db_upload_fastn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -112,6 +113,15 @@ def order_hits(hits: np.ndarray, name_rank, rec_off, score=None) -> np.ndarray:
 
 def _err():
     return lib().gm_last_error().decode("utf-8", "replace")
+
+
+def plan_describe(plan: bytes) -> str:
+    """What the library derives from a plan (per-search table, level-0 filter,
+    look-ahead targets, probes) as text.  Host side, needs no device."""
+    buf = C.create_string_buffer(1 << 16)
+    if lib().gm_plan_describe(plan, buf, len(buf)) != 0:
+        raise GpuMotifError("gm_plan_describe: " + _err())
+    return buf.value.decode()
 
 
 def plan_field(plan: bytes, idx: int) -> int:
