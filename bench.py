@@ -1,26 +1,38 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the descriptor search, in strand-nucleotides
 scanned per second (BASELINE.json: "Gnt/s scanned (both strands) per
-descriptor at 1/2/4/8 B200").
+descriptor at 1/2/4/8 B200; hits bit-exact").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gpumotif|reference]
-                    [--descr trna] [--mnt 1024]
+                    [--descr trna] [--mnt 1024] [--configs all|none|a,b,..]
 
-A step is one pass of the hot path over one batch: every start offset on both
-strands of a synthetic database of `--mnt` Mnt per GPU (i.i.d. uniform acgt,
-1 Mnt records -- SURVEY.md 8d "syn_1G"), descriptor test/trna.descr (the one
-BASELINE.json's target is quoted on).  One process per GPU; ranks own disjoint
-databases (weak scaling); no collective on the data path.
+A step is one pass of the hot path over one batch: every start offset on the
+searched strands of a synthetic database (i.i.d. uniform acgt).
+One process per GPU; ranks own disjoint databases (weak scaling); no collective
+on the data path.
 
-value  kernel + hit gather + host sort with the packed database RESIDENT in HBM
-e2e    the same call made with HOST buffers (pinned characters): H2D copy,
-       device pack, search, candidates back on the host -- every step
-Both are timed with CUDA events on the library's stream, max over ranks.
+The headline (`value`, `e2e`, `roofline`, ...) is BASELINE.json's target config:
+test/trna.descr over 1 024 x 1 Mnt per GPU.  `per_config` carries the other
+configs of BASELINE.json at their named sizes -- ire and score.1 (1 Gnt),
+trna.general (syn_ecoli: 465 x 11.8 knt + one 5.49 Mnt record), pk1 and pk_j1+2
+(1 Gnt per GPU), qu+tr (2 Gnt per GPU) -- each with
+
+  value   kernels + candidate ordering + gather, packed database RESIDENT in HBM
+  e2e     the same call made with HOST buffers (pinned characters): H2D copy,
+          device pack, search, candidates back on the host -- every step
+  parity  checked OUTSIDE the timed regions: the candidate stream of a prefix
+          against the oracle (oracle/, CPU), and the full-size candidate arrays of
+          the resident run, the end-to-end run (chunk-streamed upload, deferred
+          enumeration) and a run through a second context with small segments and
+          another tile size -- byte for byte.  A mismatch fails the bench.
+
+Timed with CUDA events on the library's stream, max over ranks.
 
 --impl reference times the reference's own CPU implementation (the binary built
 from its sources, oracle/_ref/rnamotif, else the oracle port) on the host cores.
 """
 import argparse
+import gzip
 import json
 import os
 import subprocess
@@ -33,16 +45,35 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "strand-nt scanned per second (both strands)"
 UNIT = "G strand-nt/s"
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+PLAN_DIR = os.path.join(ROOT, "rnamotif_b200", "plans")
+
+# BASELINE.json configs 2-5 (config 1's descriptor at the target's size is the headline).
+# name -> (plan, record lengths per GPU, seed, prefix records checked against the oracle)
+ECOLI = [11_800] * 465 + [5_490_000]
+CONFIGS = {
+    "ire": ("ire", [1_000_000] * 1000, 1001, 16),
+    "score.1": ("score.1", [1_000_000] * 1000, 1001, 16),
+    "trna.general": ("trna.general", ECOLI, 1003, len(ECOLI)),
+    "pk1": ("pk1", [1_000_000] * 1000, 1004, 8),
+    "pk_j1+2": ("pk_j1+2", [1_000_000] * 1000, 1004, 16),
+    "qu+tr": ("qu+tr", [1_000_000] * 2000, 1005, 16),
+}
+# descriptor file of each plan below the reference's tree (for the CPU arm)
+DESCR_FILE = {"trna.general": os.path.join("descr", "trna.general.descr")}  # (oracle/Makefile copies it from Ecoli.trna.example/)
 
 
 def load_plan(name):
-    import helpers
-    return helpers.load_plan(name)
+    """Flattened plans of the benchmark descriptors, produced by the reference's own
+    front end (tools/make_bench_plans.sh -> rnamotif_b200/host rm_plan_dump)."""
+    path = os.path.join(PLAN_DIR, name + ".plan.gz")
+    if not os.path.exists(path):  # ad-hoc profiling runs (--descr descr.quad ...): the test corpus' plans
+        path = os.path.join(ROOT, "tests", "golden", "plans", name + ".plan.gz")
+    with gzip.open(path, "rb") as fh:
+        return fh.read()
 
 
 def peaks():
@@ -50,6 +81,10 @@ def peaks():
     if os.path.exists(p):
         return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def plan_strands(plan):
+    return 2 if int(np.frombuffer(plan, dtype=np.int32, count=9)[8]) else 1
 
 
 # ------------------------------------------------------------------ CPU arm
@@ -66,9 +101,9 @@ def cpu_reference_run(descr, procs, rec_per_proc, rec_nt, seed=1001):
     rec_per_proc x rec_nt nucleotides, one process per file (what mrnamotif
     does over MPI, src/mrnamotif.c:884-921).  Returns (strand_nt, seconds, kind)."""
     ref_bin = os.path.join(REF_DIR, "rnamotif")
-    descr_file = os.path.join(REF_DIR, "data", "test", descr + ".descr")
+    descr_file = os.path.join(REF_DIR, "data", DESCR_FILE.get(descr, os.path.join("test", descr + ".descr")))
     plan = load_plan(descr)
-    strands = 2 if int(np.frombuffer(plan, dtype=np.int32, count=9)[8]) else 1
+    strands = plan_strands(plan)
     with tempfile.TemporaryDirectory() as tmp:
         files, total = [], 0
         for p in range(procs):
@@ -78,7 +113,7 @@ def cpu_reference_run(descr, procs, rec_per_proc, rec_nt, seed=1001):
         if os.path.exists(ref_bin) and os.path.exists(descr_file):
             env = dict(os.environ, EFNDATA=os.path.join(REF_DIR, "data", "efndata"))
             t0 = time.perf_counter()
-            ps = [subprocess.Popen([ref_bin, "-descr", descr + ".descr", f],
+            ps = [subprocess.Popen([ref_bin, "-descr", os.path.basename(descr_file), f],
                                    cwd=os.path.dirname(descr_file), env=env,
                                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for f in files]
             rcs = [p.wait() for p in ps]
@@ -87,7 +122,8 @@ def cpu_reference_run(descr, procs, rec_per_proc, rec_nt, seed=1001):
                 raise RuntimeError("reference rnamotif failed: %r" % rcs)
             return total * strands, dt, "reference"
         # the reference binary did not travel: time the plain-C port instead
-        from rnamotif_b200 import fastn, oracle_port
+        from rnamotif_b200 import fastn
+        from oracle import oracle_port
         dbs = [fastn.read_fastn(f) for f in files]
 
         def work(db):
@@ -166,52 +202,54 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def run_gpu_arm(args):
-    import torch
-    import torch.distributed as dist
-    from rnamotif_b200 import gpumotif
+class Bench:
+    """Buffers shared by all workloads of a run (device characters, pinned host
+    characters), timing helpers, and the measurement of one (plan, database)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; libgpumotif has no CPU path")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; libgpumotif has no CPU path")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.cap = 0
+        self.d_chars = self.h_chars = None
+        self.lut = torch.tensor(list(b"acgt"), dtype=torch.uint8, device="cuda")
 
-    plan = load_plan(args.descr)
-    strands = 2 if gpumotif.plan_field(plan, 8) else 1
-    rec_nt = 1_000_000
-    n_rec = max(1, args.mnt)
-    total = n_rec * rec_nt
-    rec_off = np.arange(n_rec + 1, dtype=np.int64) * rec_nt
-
-    # synthetic database of this rank: uniform acgt characters, generated on the
-    # device (seeded per rank), copied once to pinned host memory for the e2e leg
-    g = torch.Generator(device="cuda")
-    g.manual_seed(1001 + rank)
-    lut = torch.tensor(list(b"acgt"), dtype=torch.uint8, device="cuda")
-    d_chars = torch.empty(total, dtype=torch.uint8, device="cuda")
-    for o in range(0, total, 1 << 27):
-        n = min(1 << 27, total - o)
-        d_chars[o:o + n] = lut[torch.randint(0, 4, (n,), generator=g, device="cuda")]
-    h_chars = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-    h_chars.copy_(d_chars)
-    torch.cuda.synchronize()
-
-    ms = gpumotif.MotifSearch(plan, device=local)
-    if args.tile:
-        ms.set_tile(args.tile)
-    stream = torch.cuda.ExternalStream(ms.stream, device=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def database(self, lengths, seed):
+        """Synthetic database of this rank: uniform acgt characters generated on the
+        device (seeded per rank), copied once to pinned host memory for the e2e leg."""
+        torch = self.torch
+        rec_off = np.concatenate([[0], np.cumsum(np.asarray(lengths, dtype=np.int64))]).astype(np.int64)
+        total = int(rec_off[-1])
+        if total > self.cap:
+            self.d_chars = self.h_chars = None
+            self.cap = total
+            self.d_chars = torch.empty(total, dtype=torch.uint8, device="cuda")
+            self.h_chars = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed + self.rank)
+        for o in range(0, total, 1 << 27):
+            n = min(1 << 27, total - o)
+            self.d_chars[o:o + n] = self.lut[torch.randint(0, 4, (n,), generator=g, device="cuda")]
+        self.h_chars[:total].copy_(self.d_chars[:total])
         torch.cuda.synchronize()
+        return rec_off, total
 
-    def timed(fn, steps):
-        barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, stream, fn, steps):
+        torch = self.torch
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -219,143 +257,289 @@ def run_gpu_arm(args):
         e1.record(stream)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        barrier()
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        self.barrier()
         return float(t.item())
 
-    # ---- resident leg -------------------------------------------------------
-    ms.set_device_chars(d_chars.data_ptr(), rec_off)
-    kernel_ms, filter_ms, launches, hits_n, filter_launches, survivors = [], [], 0, 0, 0, 0
+    def all_ok(self, ok):
+        """AND of a per-rank verdict over the ranks."""
+        if self.world == 1:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
 
-    def step_resident():
-        nonlocal launches, hits_n, filter_launches, survivors
-        ms.scan(0, total, strands, copy=False)
-        st = ms.stats()
-        kernel_ms.append(st.kernel_ms)
-        filter_ms.append(st.filter_ms)
-        launches += st.n_launches
-        filter_launches += st.n_filter_launches
-        survivors = st.n_survivors
-        hits_n = st.n_hits
+    # --------------------------------------------------------------------------------
+    def measure(self, plan, rec_off, total, steps, warmup, clocks=False, prefix_recs=0, tile=0):
+        """Resident and end-to-end throughput of one plan over the database in the
+        shared buffers; parity checks outside the timed regions.  Returns a dict."""
+        from rnamotif_b200 import gpumotif
+        torch, world = self.torch, self.world
+        strands = plan_strands(plan)
+        ms = gpumotif.MotifSearch(plan, device=self.local)
+        if tile:
+            ms.set_tile(tile)
+        stream = torch.cuda.ExternalStream(ms.stream, device=torch.device("cuda", self.local))
+        res = {"strands": strands, "n_descr": ms.n_descr}
 
-    for _ in range(args.warmup):
-        step_resident()
-    kernel_ms.clear()
-    filter_ms.clear()
-    launches = filter_launches = 0
-    sampler = ClockSampler(local)
-    sampler.start()
-    t_res = timed(step_resident, args.steps)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    k_ms = float(np.mean(kernel_ms))
-    gpu_launches = launches
+        # ---- resident leg -----------------------------------------------------
+        ms.set_device_chars(self.d_chars.data_ptr(), rec_off)
+        acc = {"kernel_ms": [], "filter_ms": [], "launches": 0, "filter_launches": 0, "survivors": 0, "hits": 0}
 
-    # ---- end-to-end leg: host characters in, candidates out, every step -------
-    h2d = d2h = 0
+        def step_resident():
+            ms.scan(0, total, strands, copy=False)
+            st = ms.stats()
+            acc["kernel_ms"].append(st.kernel_ms)
+            acc["filter_ms"].append(st.filter_ms)
+            acc["launches"] += st.n_launches
+            acc["filter_launches"] += st.n_filter_launches
+            acc["survivors"] = st.n_survivors
+            acc["hits"] = st.n_hits
 
-    phases = {}
+        for _ in range(warmup):
+            step_resident()
+        acc["kernel_ms"].clear()
+        acc["filter_ms"].clear()
+        acc["launches"] = acc["filter_launches"] = 0
+        sampler = None
+        if clocks:
+            sampler = ClockSampler(self.local)
+            sampler.start()
+        t_res = self.timed(stream, step_resident, steps)
+        if sampler is not None:
+            sampler.stop_flag = True
+            sampler.join(timeout=2)
+            res["clocks"] = sampler.summary()
+        hits_res = ms.hits(copy=True)
 
-    def step_e2e():
-        nonlocal h2d, d2h
-        ms.upload_ptr(h_chars.data_ptr(), rec_off)
-        ms.scan(0, total, strands, copy=False)  # candidates are in host memory (library buffer)
-        st = ms.stats()
-        h2d, d2h = st.h2d_bytes, st.d2h_bytes
-        phases.update(h2d_ms=st.h2d_ms, pack_ms=st.pack_ms, kernel_ms=st.kernel_ms, d2h_ms=st.d2h_ms,
-                      sort_ms=st.sort_ms)
+        # ---- end-to-end leg: host characters in, candidates out, every step --------
+        e2e_info = {}
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    t_e2e = timed(step_e2e, args.steps)
+        def step_e2e():
+            ms.upload_ptr(self.h_chars.data_ptr(), rec_off)
+            ms.scan(0, total, strands, copy=False)  # candidates are in host memory (library buffer)
+            st = ms.stats()
+            e2e_info.update(h2d=st.h2d_bytes, d2h=st.d2h_bytes,
+                            phases=dict(h2d_ms=st.h2d_ms, pack_ms=st.pack_ms, kernel_ms=st.kernel_ms,
+                                        d2h_ms=st.d2h_ms, sort_ms=st.sort_ms))
 
-    work = float(total) * strands * world  # strand-nt per step, all ranks
-    value = work * args.steps / (t_res / 1e3) / 1e9
-    e2e = work * args.steps / (t_e2e / 1e3) / 1e9
+        for _ in range(max(1, min(warmup, 2))):
+            step_e2e()
+        t_e2e = self.timed(stream, step_e2e, steps)
+        hits_e2e = ms.hits(copy=True)
 
+        work = float(total) * strands * world  # strand-nt per step, all ranks
+        res.update(value=work * steps / (t_res / 1e3) / 1e9, ms_per_step=t_res / steps,
+                   e2e_value=work * steps / (t_e2e / 1e3) / 1e9, e2e_ms_per_step=t_e2e / steps,
+                   h2d=int(e2e_info["h2d"]), d2h=int(e2e_info["d2h"]), phases=e2e_info["phases"],
+                   t_res=t_res, acc=acc, total=total, candidates=int(acc["hits"]))
+
+        # ---- parity, outside the timed regions -----------------------------------------
+        par = {"full_candidates": int(len(hits_res))}
+        same = len(hits_res) == len(hits_e2e) and hits_res.tobytes() == hits_e2e.tobytes()
+        # a second context: small worklist segments (several filter/enumeration launch
+        # pairs, no deferred enumeration) and another tile size
+        os.environ["GPUMOTIF_SEG_NT"] = str(48 << 20)
+        try:
+            ms2 = gpumotif.MotifSearch(plan, device=self.local)
+        finally:
+            del os.environ["GPUMOTIF_SEG_NT"]
+        ms2.set_tile(416)
+        ms2.set_device_chars(self.d_chars.data_ptr(), rec_off)
+        hits_alt = ms2.scan(0, total, strands, copy=True)
+        same = same and len(hits_alt) == len(hits_res) and hits_alt.tobytes() == hits_res.tobytes()
+        par["full_equal_across_paths"] = self.all_ok(same)
+        if prefix_recs > 0 and self.rank == 0:
+            n_pre = min(prefix_recs, len(rec_off) - 1)
+            pre_nt = int(rec_off[n_pre])
+            hits_pre = ms2.scan(0, pre_nt, strands, copy=True)
+            ok, n_ref, W = oracle_check(plan, self.h_chars[:pre_nt].numpy(), rec_off[:n_pre + 1], strands, hits_pre)
+            par.update(prefix_nt=pre_nt, prefix_candidates=int(n_ref), prefix_equal_oracle=bool(ok))
+            res["pair_evals_per_strand_nt"] = W
+        ms2.close()
+        if self.world > 1:
+            self.dist.barrier()
+        res["parity"] = par
+        ms.close()
+        return res
+
+
+def oracle_check(plan, chars, rec_off, strands, gpu_hits):
+    """The oracle (oracle/, plain C, CPU) over the same records, on all host cores
+    (records dealt out to threads; ctypes releases the GIL).  Returns (equal,
+    candidates of the oracle, pair-rule evaluations per start)."""
+    from oracle import oracle_port
+    n_rec = len(rec_off) - 1
+    order = sorted(range(n_rec), key=lambda r: -(rec_off[r + 1] - rec_off[r]))
+    n_thr = max(1, min(os.cpu_count() or 1, n_rec))
+    groups = [[] for _ in range(n_thr)]
+    load = [0] * n_thr
+    for r in order:  # longest first onto the least loaded thread
+        k = load.index(min(load))
+        groups[k].append(r)
+        load[k] += int(rec_off[r + 1] - rec_off[r])
+    out = {}
+    evals = [0, 0]
+    lock = threading.Lock()
+
+    def work(recs):
+        for r in recs:
+            seq = np.ascontiguousarray(chars[rec_off[r]:rec_off[r + 1]])
+            h, st = oracle_port.scan_db(plan, seq, np.array([0, len(seq)], dtype=np.int64), strands == 2,
+                                        cap_hits=1 << 14)
+            h = h.copy()
+            h["rec"] = r
+            with lock:
+                out[r] = h
+                evals[0] += st.n_pair_evals
+                evals[1] += st.n_starts
+
+    th = [threading.Thread(target=work, args=(g,)) for g in groups if g]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    parts = [out[r] for r in range(n_rec) if len(out[r])]
+    ref = np.concatenate(parts) if parts else gpu_hits[:0]
+    ok = len(ref) == len(gpu_hits)
+    if ok and len(ref):
+        for f in ("rec", "szero", "seq", "comp", "lctx_off", "lctx_len", "rctx_off", "rctx_len"):
+            ok = ok and bool((ref[f] == gpu_hits[f]).all())
+        for f in ("off", "len", "mpr", "mm"):
+            ok = ok and bool((ref["el"][f] == gpu_hits["el"][f]).all())
+    return ok, len(ref), evals[0] / max(evals[1], 1)
+
+
+def dominant_kernel(res, steps, n_descr):
+    """Which kernel dominates a measured step, its per-launch duration (CUDA events the
+    library records around its launches) and its algorithmic bytes per launch."""
+    acc, total, t_res = res["acc"], res["total"], res["t_res"]
+    k_sum, f_sum = float(np.sum(acc["kernel_ms"])), float(np.sum(acc["filter_ms"]))
+    fl, gl = acc["filter_launches"], acc["launches"]
+    per_step_fl = max(fl / steps, 1)
+    if fl > 0 and f_sum < 0.5 * k_sum:
+        name = "gm_dfs_kernel<FULL> (enumeration of the filter's survivors)"
+        ms = (k_sum - f_sum) / fl
+        alg = acc["survivors"] / per_step_fl * (32 + 64) + acc["hits"] * (32 + 8 * n_descr) / per_step_fl
+        share = (k_sum - f_sum) / t_res
+    elif fl > 0:
+        name = "gm_search_kernel<1,FULL,PF> (level-0 sieve / prefilter)"
+        ms = f_sum / fl
+        alg = total * steps / fl * 0.5 + acc["survivors"] / per_step_fl * 32
+        share = f_sum / t_res
+    else:
+        name = "gm_search_kernel<0,FULL,PF> (fused filter + enumeration)"
+        ms = k_sum / steps / max(gl / steps, 1)
+        alg = total * steps / max(gl, 1) * 0.5 + acc["hits"] * (32 + 8 * n_descr) / max(gl / steps, 1)
+        share = k_sum / t_res
+    return name, ms, alg, share, k_sum / steps, (f_sum / steps if fl > 0 else None)
+
+
+def run_gpu_arm(args):
+    B = Bench(args)
+    rank, world = B.rank, B.world
+    pk, which = peaks()
+
+    # ---- headline: BASELINE.json's target config ----------------------------------
+    plan = load_plan(args.descr)
+    rec_off, total = B.database([1_000_000] * max(1, args.mnt), 1001)
+    res = B.measure(plan, rec_off, total, args.steps, args.warmup, clocks=True,
+                    prefix_recs=(16 if not args.no_parity else 0), tile=args.tile)
+    name, dom_ms, alg, share, k_ms, f_ms = dominant_kernel(res, args.steps, res["n_descr"])
+    line = None
     if rank == 0:
-        pk, which = peaks()
-        # The dominant kernel.  On the worklist path (strong level-0 filter, e.g. trna)
-        # it is the sieve kernel gm_search_kernel<1,*,2>: it alone reads the packed
-        # database (0.5 B per nt, once for both strands) and writes the worklist; the
-        # enumeration kernel gm_dfs_kernel touches only the survivors' windows.  On the
-        # fused path one kernel does both.  Its average launch duration comes from CUDA
-        # events the library records around every launch on its stream.
-        split = filter_launches > 0
-        if split and float(np.sum(filter_ms)) < 0.5 * float(np.sum(kernel_ms)):
-            # worklist path whose enumeration kernel dominates (weak filters: pk1, trna.general)
-            dom_name = "gm_dfs_kernel<FULL> (enumeration of the filter's survivors)"
-            dom_ms = (float(np.sum(kernel_ms)) - float(np.sum(filter_ms))) / filter_launches
-            per_launch_nt = total * args.steps / filter_launches
-            alg_bytes = survivors / max(filter_launches / args.steps, 1) * (32 + 64) + \
-                hits_n * (32 + 8 * ms.n_descr) / max(filter_launches / args.steps, 1)
-            split = False
-            filter_share = (float(np.sum(kernel_ms)) - float(np.sum(filter_ms))) / t_res
-        elif split:
-            filter_share = float(np.sum(filter_ms)) / t_res
-            dom_name = "gm_search_kernel<1,FULL,PF> (level-0 sieve / prefilter)"
-            dom_ms = float(np.sum(filter_ms)) / filter_launches            # per launch
-            per_launch_nt = total * args.steps / filter_launches
-            alg_bytes = per_launch_nt * 0.5 + survivors / max(filter_launches / args.steps, 1) * 32
-        else:
-            filter_share = float(np.sum(kernel_ms)) / t_res
-            dom_name = "gm_search_kernel<0,FULL,PF> (fused filter + enumeration)"
-            dom_ms = k_ms / max(gpu_launches / args.steps, 1)
-            per_launch_nt = total * args.steps / max(gpu_launches, 1)
-            alg_bytes = per_launch_nt * 0.5 + hits_n * (32 + 8 * ms.n_descr) / max(gpu_launches / args.steps, 1)
-        achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+        achieved = alg / (dom_ms / 1e3) / 1e9
         traffic = None
-        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        issue_ncu = None
+        tj = os.path.join(ROOT, "profiles", "r2_sieve_kernel.json")
         if os.path.exists(tj):
             t = json.load(open(tj))
-            if t["workload"] == {"descr": args.descr, "mnt": args.mnt}:
+            if t.get("workload") == {"descr": args.descr, "mnt": args.mnt}:
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]  # bytes per launch, ncu
-        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": alg_bytes,
-                "peak_source": which,
-                "kernel": dom_name, "kernel_ms": dom_ms, "kernel_share_of_step": filter_share,
-                "all_kernels_ms_per_step": k_ms,
-                "note": "the search is integer-issue bound, not HBM bound (SURVEY.md F8); see issue and profiles/"}
+                issue_ncu = t.get("issue")
+        sm_clk = (res["clocks"]["sm_mhz"] or 1965.0) * 1e6
+        lane_peak = 148 * 128 * sm_clk
+        W = res.get("pair_evals_per_strand_nt")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_res / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"test/{args.descr}.descr over syn_{args.mnt}M: {n_rec} x 1 Mnt uniform acgt per GPU, "
-                                   f"{strands} strand(s)", "l2": "input (packed) larger than L2" if total / 2 > 126e6
+            "config": {"workload": f"test/{args.descr}.descr over syn_{args.mnt}M: {args.mnt} x 1 Mnt uniform acgt per GPU, "
+                                   f"{res['strands']} strand(s)",
+                       "l2": "input (packed) larger than L2" if total / 2 > 126e6
                        else "input smaller than L2; each step re-reads it after the hit gather",
-                       "candidates_per_step_rank0": int(hits_n)},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": t_e2e / args.steps, "phases_ms_last_step": phases},
-            "gpu_launches": int(gpu_launches),
-            "roofline": roof,
-            "clocks": sampler.summary(),
+                       "candidates_per_step_rank0": res["candidates"]},
+            "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": res["h2d"],
+                    "d2h_bytes_per_step": res["d2h"], "ms_per_step": res["e2e_ms_per_step"],
+                    "phases_ms_last_step": res["phases"]},
+            "gpu_launches": int(res["acc"]["launches"]),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": alg,
+                         "peak_source": which, "kernel": name, "kernel_ms": dom_ms, "kernel_share_of_step": share,
+                         "all_kernels_ms_per_step": k_ms,
+                         "note": "the search is integer-issue bound, not HBM bound (SURVEY.md F8); see issue and profiles/"},
+            "parity": res["parity"],
+            "clocks": res["clocks"],
         }
+        if W is not None:
+            line["issue"] = {"pair_evals_per_strand_nt": W,
+                             "pair_evals_per_s": W * total * res["strands"] / (k_ms / 1e3),
+                             "int_lane_peak_per_s": lane_peak,
+                             "frac_of_lane_peak": W * total * res["strands"] / (k_ms / 1e3) / lane_peak,
+                             "ncu": issue_ncu,
+                             "note": "the reference's pair-rule evaluations per strand-nt (oracle count on the parity prefix) x "
+                                     "measured strand-nt/s = algorithm-level rate; `ncu` = issue-slot utilisation of the "
+                                     "dominant kernel from the committed capture (profiles/r2_sieve_kernel.json)"}
+
+    # ---- the other configs of BASELINE.json ------------------------------------------
+    per_config = []
+    names = [] if args.configs == "none" else (list(CONFIGS) if args.configs == "all" else args.configs.split(","))
+    for cname in names:
+        pname, lengths, seed, pre = CONFIGS[cname]
+        cplan = load_plan(pname)
+        c_off, c_total = B.database(lengths, seed)
+        r = B.measure(cplan, c_off, c_total, args.cfg_steps, args.cfg_warmup,
+                      prefix_recs=(pre if not args.no_parity else 0))
+        if rank != 0:
+            continue
+        kname, kms, kalg, kshare, kk_ms, kf_ms = dominant_kernel(r, args.cfg_steps, r["n_descr"])
+        entry = {
+            "config": cname, "workload": f"{pname}.descr over {len(lengths)} records, {c_total / 1e6:.1f} Mnt per GPU "
+                                         f"(seed {seed}), {r['strands']} strand(s)",
+            "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+            "e2e": {"value": r["e2e_value"], "ms_per_step": r["e2e_ms_per_step"], "h2d_bytes_per_step": r["h2d"],
+                    "d2h_bytes_per_step": r["d2h"]},
+            "steps": args.cfg_steps, "warmup": args.cfg_warmup,
+            "candidates_per_step_rank0": r["candidates"], "survivors_of_level0_rank0": int(r["acc"]["survivors"]),
+            "kernel": kname, "kernel_ms": kms, "kernel_share_of_step": kshare,
+            "kernels_ms_per_step": kk_ms, "filter_ms_per_step": kf_ms,
+            "hbm_frac": kalg / (kms / 1e3) / 1e9 / pk["hbm_gbs"],
+            "parity": r["parity"],
+        }
+        W = r.get("pair_evals_per_strand_nt")
+        if W is not None:
+            lane_peak = 148 * 128 * 1965.0e6
+            entry["useful_work"] = {"pair_evals_per_strand_nt": W,
+                                    "frac_of_lane_peak": W * c_total * r["strands"] / (kk_ms / 1e3) / lane_peak}
+        per_config.append(entry)
+
+    if rank == 0:
+        if per_config:
+            line["per_config"] = per_config
+        bad = [e["config"] for e in per_config if not all(v for k, v in e["parity"].items() if k.endswith("equal_oracle") or k.startswith("full_equal"))]
+        hp = line["parity"]
+        if not hp.get("full_equal_across_paths", True) or not hp.get("prefix_equal_oracle", True):
+            bad.append(args.descr)
         if world == 1 and not args.no_cpu:
             w, dt, kind = cpu_reference_run(args.descr, 1, 16, 1_000_000)
             line["cpu_baseline"] = {"value": w / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": "16 x 1 Mnt synthetic acgt, one process, default flags"}
-            # the reference's pair-rule evaluations per strand-nt on this input class (oracle count)
-            try:
-                from rnamotif_b200 import oracle_port, synth
-                ids, seq, off = synth.random_records(5, [200_000])
-                _, st = oracle_port.scan_db(plan, seq, off, strands == 2)
-                W = st.n_pair_evals / max(st.n_starts, 1)
-                sm_clk = (line["clocks"]["sm_mhz"] or 1965.0) * 1e6
-                lane_peak = 148 * 128 * sm_clk
-                line["issue"] = {"pair_evals_per_strand_nt": W,
-                                 "pair_evals_per_s": W * total * strands / (k_ms / 1e3),
-                                 "int_lane_peak_per_s": lane_peak,
-                                 "frac_of_lane_peak": W * total * strands / (k_ms / 1e3) / lane_peak,
-                                 "note": "the reference's pair-rule evaluations per strand-nt (oracle count) x measured "
-                                         "strand-nt/s; the sieve does the same tests 32 starts to a word, so this is "
-                                         "the algorithm-level rate, not an instruction count"}
-            except Exception as e:
-                line["issue"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
-    ms.close()
+        if bad:
+            print("bench.py: PARITY FAILED for " + ", ".join(bad), file=sys.stderr)
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
+    if rank == 0 and bad:
+        sys.exit(3)
 
 
 def main():
@@ -365,8 +549,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gpumotif", choices=["gpumotif", "reference"])
     ap.add_argument("--descr", default="trna")
-    ap.add_argument("--mnt", type=int, default=1024, help="Mnt of synthetic sequence per GPU")
+    ap.add_argument("--mnt", type=int, default=1024, help="Mnt of synthetic sequence per GPU (headline)")
+    ap.add_argument("--configs", default="all", help="per_config block: all, none, or a comma list of "
+                    + ",".join(CONFIGS))
+    ap.add_argument("--cfg-steps", type=int, default=2)
+    ap.add_argument("--cfg-warmup", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle prefix checks")
     ap.add_argument("--tile", type=int, default=0, help="starts per tile (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":

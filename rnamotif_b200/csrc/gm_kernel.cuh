@@ -153,6 +153,7 @@ __host__ __device__ inline size_t plan_smem_bytes(const DevParams &par)
 	n += ((size_t)par.n_lentab + 15) & ~(size_t)15;
 	n += (par.n_sites * sizeof(gm_site_t) + 15) & ~(size_t)15;
 	n += ((size_t)par.n_descr * 4 + 15) & ~(size_t)15;
+	n += 2 * (((size_t)(par.n_descr + 1) * 4 + 15) & ~(size_t)15);
 	return n;
 }
 
@@ -161,6 +162,7 @@ struct StagedPlan {
 	DevSearch *ds;
 	const gm_pairset_t *ps;
 	uint32_t *elmm;   // (minlen, maxlen) per element, packed (find_minlen / find_maxlen)
+	int *pmin, *pmax; // their prefix sums: pmin[d] = sum of minlen over elements < d
 };
 
 __device__ __forceinline__ void copy_words(void *dst, const void *src, int n_words, int tid, int nt)
@@ -184,6 +186,8 @@ __device__ __forceinline__ uint8_t *stage_plan(uint8_t *p, const ScanArgs &A, in
 	uint8_t *lt = p;                                        p += ((size_t)par.n_lentab + 15) & ~(size_t)15;
 	gm_site_t *si = reinterpret_cast<gm_site_t *>(p);       p += (par.n_sites * sizeof(gm_site_t) + 15) & ~(size_t)15;
 	uint32_t *elmm = reinterpret_cast<uint32_t *>(p);       p += ((size_t)par.n_descr * 4 + 15) & ~(size_t)15;
+	int *pmin = reinterpret_cast<int *>(p);                 p += ((size_t)(par.n_descr + 1) * 4 + 15) & ~(size_t)15;
+	int *pmax = reinterpret_cast<int *>(p);                 p += ((size_t)(par.n_descr + 1) * 4 + 15) & ~(size_t)15;
 	for (int i = tid; i < (int)(sizeof(DevParams) / 4); i += nt)
 		reinterpret_cast<uint32_t *>(&pv->par)[i] = reinterpret_cast<const uint32_t *>(&A.par)[i];
 	copy_words(ds, A.ds, par.n_searches * (int)(sizeof(DevSearch) / 4), tid, nt);
@@ -197,6 +201,15 @@ __device__ __forceinline__ uint8_t *stage_plan(uint8_t *p, const ScanArgs &A, in
 	for (int i = tid; i < par.n_descr; i += nt)
 		elmm[i] = pk16(pl->elems[i].minlen, pl->elems[i].maxlen);
 	if (tid == 0) {
+		int a = 0, b = 0;
+		for (int i = 0; i <= par.n_descr; i++) {
+			pmin[i] = a;
+			pmax[i] = b;
+			if (i < par.n_descr) {
+				a += pl->elems[i].minlen;
+				b += pl->elems[i].maxlen;
+			}
+		}
 		pv->elems = el;
 		pv->pairsets = ps;
 		pv->regex = rx;
@@ -214,6 +227,8 @@ __device__ __forceinline__ uint8_t *stage_plan(uint8_t *p, const ScanArgs &A, in
 	sp.ds = ds;
 	sp.ps = ps;
 	sp.elmm = elmm;
+	sp.pmin = pmin;
+	sp.pmax = pmax;
 	return p;
 }
 
@@ -389,35 +404,41 @@ __device__ __noinline__ bool sink_sites(const Lane &L)
 	return true;
 }
 
-// the hit sink up to RM_score, src/find_motif.c:362-372
-__device__ __noinline__ void sink(Lane &L, const ScanArgs &A)
+// The hit sink up to RM_score, src/find_motif.c:362-372, in two parts.  The lane
+// that completed a candidate runs the sink's filters (sink_pass); the hit record is
+// then written by the whole warp at the next converged point of the machine loop
+// (sink_write: lane d formats element d), because a record is 8 + 2 n_descr words and
+// candidates can be frequent (trna.general: two per thousand strand-nt).
+__device__ __noinline__ bool sink_pass(Lane &L, int ctx[4])
 {
-	int ctx[4];
+	ctx[0] = ctx[1] = ctx[2] = ctx[3] = -1;
 	if (PV.par.strict_helices && !sink_strict(L))
-		return;
-	if (!sink_context(L, ctx))
-		return;
+		return false;
+	if ((PV.lctx.present || PV.rctx.present) && !sink_context(L, ctx))
+		return false;
 	if (PV.n_sites > 0 && !sink_sites(L))
-		return;
-	unsigned long long slot = atomicAdd(A.hit_count, 1ull);
-	uint32_t seq = L.seq++;
+		return false;
+	return true;
+}
+
+// all 32 lanes; `src` = the lane whose candidate is written, Ls = that lane's state
+__device__ __forceinline__ void sink_write(const Lane &Ls, const ScanArgs &A, int lane, unsigned long long slot,
+	uint32_t rec, int szero, uint32_t seq, int comp, int c0, int c1, int c2, int c3)
+{
+	const Lane &L = Ls; // (for PV)
 	if (slot >= A.hit_cap)
 		return; // counted; the host grows the buffer and re-runs
 	uint32_t *h = A.hits + slot * (unsigned long long)A.stride_words;
-	h[0] = L.rec;
-	h[1] = (uint32_t)L.szero;
-	h[2] = seq;
-	h[3] = (uint32_t)L.comp;
-	h[4] = (uint32_t)ctx[0];
-	h[5] = (uint32_t)ctx[1];
-	h[6] = (uint32_t)ctx[2];
-	h[7] = (uint32_t)ctx[3];
-	for (int d = 0; d < L.ND; d++) {
-		const uint32_t el = el_word(L, d, PV.par.lite != 0);
+	if (lane < 8)
+		h[lane] = lane == 0 ? rec : lane == 1 ? (uint32_t)szero : lane == 2 ? seq : lane == 3 ? (uint32_t)comp :
+			lane == 4 ? (uint32_t)c0 : lane == 5 ? (uint32_t)c1 : lane == 6 ? (uint32_t)c2 : (uint32_t)c3;
+	const bool lite = PV.par.lite != 0;
+	for (int d = lane; d < Ls.ND; d += 32) {
+		const uint32_t el = el_word(Ls, d, lite);
 		int mpr, mm;
-		if (PV.par.lite) {
+		if (lite) {
 			// counts live in the frames: a helix head keeps its mispairs, an ss its mismatches
-			const int f1 = lo16(L_FR(L, PV.par.elsrc[d], 1));
+			const int f1 = lo16(L_FR(Ls, PV.par.elsrc[d], 1));
 			if (PV.elems[d].type == GM_SS) {
 				mpr = 0;
 				mm = f1;
@@ -426,11 +447,11 @@ __device__ __noinline__ void sink(Lane &L, const ScanArgs &A)
 				mm = 0;
 			}
 		} else {
-			const uint32_t em = L_EM(L, d);
+			const uint32_t em = L_EM(Ls, d);
 			mpr = lo16(em);
 			mm = hi16(em);
 		}
-		h[8 + 2 * d] = (uint32_t)(L.szero + lo16(el));
+		h[8 + 2 * d] = (uint32_t)(szero + lo16(el));
 		h[9 + 2 * d] = (uint32_t)(hi16(el) & 0xffff) | ((uint32_t)(mpr & 0xff) << 16) |
 			((uint32_t)(mm & 0xff) << 24);
 	}
@@ -557,24 +578,25 @@ __device__ __noinline__ void wx_finish_mm(Lane &L, const DevSearch &S, int s5, i
 		;
 }
 
-// find_minlen / find_maxlen, src/find_motif.c:642-665
-__device__ __noinline__ int pk_minlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
+// find_minlen / find_maxlen, src/find_motif.c:642-665, over elements fd..ld of the
+// pseudoknot of search S, as (min, max) packed: prefix sums over the static lengths,
+// corrected for the elements that can be matched at this point (DevSearch::pkm_off).
+__device__ __noinline__ uint32_t pk_range(const Lane &L, const StagedPlan &sp, const DevSearch &S, int fd, int ld)
 {
-	int v = 0;
-	for (int d = fd; d <= ld; d++) {
+	if (fd > ld)
+		return 0;
+	int mn = sp.pmin[ld + 1] - sp.pmin[fd], mx = sp.pmax[ld + 1] - sp.pmax[fd];
+	for (int i = 0; i < S.pkm_n; i++) {
+		const int d = PV.par.pk_m[S.pkm_off + i];
+		if (d < fd || d > ld)
+			continue;
 		const int ml = hi16(L_EL(L, d)); // only plans that keep element words get here
-		v += ml != GM_UNDEF ? ml : lo16(elmm[d]);
+		if (ml != GM_UNDEF) {
+			mn += ml - lo16(sp.elmm[d]);
+			mx += ml - hi16(sp.elmm[d]);
+		}
 	}
-	return v;
-}
-__device__ __noinline__ int pk_maxlen(const Lane &L, const uint32_t *elmm, int fd, int ld)
-{
-	int v = 0;
-	for (int d = fd; d <= ld; d++) {
-		const int ml = hi16(L_EL(L, d));
-		v += ml != GM_UNDEF ? ml : hi16(elmm[d]);
-	}
-	return v;
+	return pk16(mn, min(mx, 30000));
 }
 
 // match_phlx, src/find_motif.c:1114-1181

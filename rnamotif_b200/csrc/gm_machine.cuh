@@ -414,7 +414,6 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	StagedPlan sp;
 	uint8_t *p = stage_plan(smem_raw, A, tid, nt, sp);
 	DevSearch *sm_ds = sp.ds;
-	uint32_t *sm_elmm = sp.elmm;
 	uint64_t *sm_litB = reinterpret_cast<uint64_t *>(p);       p += LIT ? 16 * 8 : 0; // literal prefilter class masks
 	uint8_t *wp = p + (size_t)warp * warp_bytes;               p += (size_t)nwarps * warp_bytes;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);
@@ -1167,7 +1166,6 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	StagedPlan sp;
 	uint8_t *p = stage_plan(smem_raw, A, tid, nt, sp);
 	DevSearch *sm_ds = sp.ds;
-	uint32_t *sm_elmm = sp.elmm;
 	uint8_t *sm_win = p;                                       p += (size_t)nt * wstride;
 	uint32_t *sm_bits = reinterpret_cast<uint32_t *>(p);       p += (size_t)nt * A.par.win_bits * 4;
 	uint32_t *sm_state = reinterpret_cast<uint32_t *>(p);

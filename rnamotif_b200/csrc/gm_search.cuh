@@ -73,11 +73,16 @@ struct DevSearch {
 	// 3' strand) | off << 2 (10 bits) | len << 12 (8) | regex << 20 (5) | mismatch << 25 (4)
 	int n_probe;
 	unsigned probe[4];
+	// pseudoknot helix: the elements of its pseudoknot that can be matched when the
+	// search reaches it (the strands of the helices searched before it), as a slice of
+	// DevParams::pk_m -- find_minlen / find_maxlen are prefix sums corrected for those
+	int pkm_off, pkm_n;
 };
-static_assert(sizeof(DevSearch) == 39 * 4, "DevSearch is staged with an odd word stride");
+static_assert(sizeof(DevSearch) == 41 * 4, "DevSearch is staged with an odd word stride");
 
 #define GM_MAX_DUPS 8
 #define GM_MAX_CHAIN 40
+#define GM_MAX_PKM 64
 
 struct DevParams {
 	int n_searches, n_descr;
@@ -105,6 +110,7 @@ struct DevParams {
 	// descriptor's elements from last to first as steps (min, max, allowed bases,
 	// exception budget per length); a start survives only if every element can be laid
 	// out contiguously behind it with its strand made of bases that can pair at all.
+	int pk_m[GM_MAX_PKM];   // see DevSearch::pkm_off
 	int chain;              // number of steps, 0 = off
 	unsigned chain_w0[GM_MAX_CHAIN]; // min (12 bits) | max << 12 (12) | allowed bases << 24 (4) | both ends << 28 | constrained << 29
 	unsigned chain_w1[GM_MAX_CHAIN]; // budget of length min + i in bits 2i, 2i+1 (3 = no limit)

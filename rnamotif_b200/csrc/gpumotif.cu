@@ -513,6 +513,34 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 			}
 		}
 	}
+	// pseudoknot helices: which elements of their pseudoknot can be matched when the
+	// search gets to them (DevSearch::pkm_off)
+	{
+		int n_pkm = 0;
+		for (int s = 0; s < NS; s++) {
+			DevSearch &S = ds[s];
+			S.pkm_off = n_pkm;
+			S.pkm_n = 0;
+			if (S.kind != K_PK)
+				continue;
+			const gm_elem_t &e = pl->elems[S.d];
+			const int d0 = pl->scopes[e.scopes], dn = pl->scopes[e.scopes + e.n_scopes - 1];
+			if (d0 < 0 || dn >= ND || d0 > dn)
+				return fail("search %d: bad pseudoknot range", s);
+			for (int k = d0; k <= dn; k++) {
+				const gm_elem_t &ek = pl->elems[k];
+				int own = ek.searchno;
+				if (own < 0 && ek.n_mates >= 1 && ek.mates[0] >= 0 && ek.mates[0] < ND)
+					own = pl->elems[ek.mates[0]].searchno;
+				if (own >= 0 && own < s) {
+					if (n_pkm >= GM_MAX_PKM)
+						return fail("search %d: pseudoknot too complex for the device tables", s);
+					par->pk_m[n_pkm++] = k;
+					S.pkm_n++;
+				}
+			}
+		}
+	}
 	// level-0 prefilter: the first helix head, if everything before it is a
 	// fixed-length single strand without seq= (then its 5' start is known)
 	par->pf_search = -1;
@@ -1167,7 +1195,11 @@ static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src
 		return -1;
 	// chunk size: at least 64 Mnt, at most 8 chunks (every chunk costs a kernel
 	// launch with its own ramp and tail), a multiple of 16 nucleotides
-	int64_t chunk = std::max<int64_t>((int64_t)64 << 20, (n + 7) / 8);
+	// (GPUMOTIF_CHUNK_NT lowers the 64 Mnt floor: tests run the chunk-streamed scan on small inputs)
+	int64_t floor_nt = (int64_t)64 << 20;
+	if (getenv("GPUMOTIF_CHUNK_NT") != NULL && atoll(getenv("GPUMOTIF_CHUNK_NT")) >= 4096)
+		floor_nt = atoll(getenv("GPUMOTIF_CHUNK_NT"));
+	int64_t chunk = std::max<int64_t>(floor_nt, (n + 7) / 8);
 	chunk = (chunk + 15) & ~(int64_t)15;
 	const int n_chunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
 	while ((int)c->chunk_ev.size() < n_chunks) {

@@ -25,6 +25,15 @@ def load_plan(name: str) -> bytes:
         return fh.read()
 
 
+def load_extra_plan(name: str):
+    """Plans without a committed candidate stream (tools/make_bench_plans.sh)."""
+    path = os.path.join(GOLDEN, "plans_extra", name + ".plan.gz")
+    if not os.path.exists(path):
+        return None
+    with gzip.open(path, "rb") as fh:
+        return fh.read()
+
+
 def load_cands(name: str):
     z = np.load(os.path.join(GOLDEN, "cands", name + ".npz"))
     return z["head"], z["els"], z["ctx"]

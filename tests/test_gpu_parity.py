@@ -4,7 +4,8 @@ candidate streams of the reference binary.  Bar: bit-exact (integer work)."""
 import numpy as np
 import pytest
 
-from rnamotif_b200 import gpumotif, oracle_port, synth
+from oracle import oracle_port
+from rnamotif_b200 import gpumotif, synth
 import helpers
 
 pytestmark = pytest.mark.gpu
@@ -138,8 +139,9 @@ def test_worklist_overflow_is_recovered(monkeypatch):
 
 
 @pytest.mark.parametrize("knob", ["GPUMOTIF_NO_SIEVE", "GPUMOTIF_NO_DEEP", "GPUMOTIF_NO_DEEP2", "GPUMOTIF_NO_TAIL",
-                                  "GPUMOTIF_NO_LITERAL", "GPUMOTIF_HOST_SORT"])
-@pytest.mark.parametrize("name", ["trna", "ire", "pk1"])
+                                  "GPUMOTIF_NO_LITERAL", "GPUMOTIF_HOST_SORT", "GPUMOTIF_NO_LOOK", "GPUMOTIF_NO_PROBE",
+                                  "GPUMOTIF_NO_CHAIN"])
+@pytest.mark.parametrize("name", ["trna", "ire", "pk1", "pk_j1+2", "qu+tr"])
 def test_filters_are_output_neutral(name, knob, monkeypatch):
     """Every level-0 filter and look-ahead only prunes what cannot reach the hit
     sink, and the device-side ordering equals the host's: with any of them switched
@@ -169,3 +171,89 @@ def test_start_count_matches_oracle(name):
     n = ms.stats().n_starts
     ms.close()
     assert n == ost.n_starts, f"{name}: {n} starts vs oracle {ost.n_starts}"
+
+
+@pytest.mark.parametrize("seg", ["default", "small"])
+@pytest.mark.parametrize("name", ["trna", "descr.trna.general", "pk1", "pk_j1+2", "qu+tr", "score.1"])
+def test_chunk_streamed_scan_matches_oracle(name, seg, monkeypatch):
+    """The first scan after an upload runs chunk by chunk behind the copy (launch():
+    stream_in), on the worklist path with the enumeration deferred to one launch at
+    the end (defer_dfs) unless the range spans several segments; later scans of the
+    same upload take the plain path with a segment size grown from the measured
+    survivor rate.  At bench sizes these paths carry the headline number; here they
+    are forced on a small input (GPUMOTIF_CHUNK_NT) and checked against the oracle."""
+    monkeypatch.setenv("GPUMOTIF_CHUNK_NT", "16384")
+    if seg == "small":
+        monkeypatch.setenv("GPUMOTIF_SEG_NT", "50000")
+    plan = helpers.load_plan(name)
+    rng = np.random.default_rng(5)
+    lengths = list(rng.integers(0, 6000, size=40)) + [150000, 3, 70000]
+    ids, seq, off = synth.random_records(17, lengths, planted=True, iupac_rate=0.002)
+    both = bool(gpumotif.plan_field(plan, 8))
+    ref, _ = oracle_port.scan_db(plan, seq, off, both)
+    ms = gpumotif.MotifSearch(plan)
+    first = ms.find_motif(seq, off)          # fresh upload: chunk-streamed
+    n_first = ms.stats().n_launches
+    second = ms.scan()                        # same upload again: plain path, grown segments
+    third = ms.find_motif(seq, off)           # and a fresh upload with the settled segment size
+    ms.close()
+    assert n_first >= 2, "the upload should have been cut into several chunks"
+    helpers.assert_same_hits(first, ref, f"{name}: chunk-streamed scan")
+    helpers.assert_same_hits(second, ref, f"{name}: rescan")
+    helpers.assert_same_hits(third, ref, f"{name}: second upload")
+
+
+def test_two_contexts_with_different_plans_interleaved():
+    """Contexts share nothing (each has its own device copy of the plan): scans of two
+    different descriptors launched back to back on one device, finished in the other
+    order, both give their oracle's stream."""
+    ids, seq, off = synth.random_records(41, [60000, 500, 90000, 12], planted=True, iupac_rate=0.002)
+    names = ["trna", "pk1", "qu+tr"]
+    plans = [helpers.load_plan(n) for n in names]
+    refs = [oracle_port.scan_db(p, seq, off, bool(gpumotif.plan_field(p, 8)))[0] for p in plans]
+    ctxs = [gpumotif.MotifSearch(p) for p in plans]
+    for _ in range(2):
+        for c in ctxs:
+            c.upload(seq, off)
+        for c in ctxs:
+            c.scan_launch()
+        for c, r, n in reversed(list(zip(ctxs, refs, names))):
+            c.scan_finish()
+            helpers.assert_same_hits(c.hits(), r, f"{n} interleaved")
+    for c in ctxs:
+        c.close()
+
+
+def test_setters_refuse_while_a_scan_is_in_flight():
+    ids, seq, off = synth.random_records(3, [30000], planted=True)
+    ms = gpumotif.MotifSearch(helpers.load_plan("trna"))
+    ms.upload(seq, off)
+    ms.scan_launch()
+    with pytest.raises(gpumotif.GpuMotifError):
+        ms.set_tile(256)
+    with pytest.raises(gpumotif.GpuMotifError):
+        ms.set_hit_capacity(1 << 12)
+    ms.scan_finish()
+    ms.set_tile(256)
+    ms.close()
+
+
+def test_hit_dense_input_and_long_windows():
+    """Descriptors of the reference's corpus whose candidate volume or window kept
+    them out of the committed goldens (tests/golden/manifest.json), on inputs small
+    enough for the oracle: mpr (mispair-tolerant hairpin: tens of candidates per
+    hundred nucleotides), hlx.gf.iu / phlx.pfrac (unbounded interior: the window is
+    the 6000-nt default), eloop."""
+    for name, n in (("descr.mpr", 6000), ("descr.hlx.gf.iu", 9000), ("descr.phlx.pfrac", 9000),
+                    ("descr.pk.gf.iu", 7000), ("descr.eloop", 9000)):
+        plan = helpers.load_extra_plan(name)
+        if plan is None:
+            pytest.skip("plan of %s not committed" % name)
+        ids, seq, off = synth.random_records(9, [n, 300, n // 2], planted=True, iupac_rate=0.001)
+        both = bool(gpumotif.plan_field(plan, 8))
+        ref, _ = oracle_port.scan_db(plan, seq, off, both, cap_hits=1 << 22)
+        ms = gpumotif.MotifSearch(plan)
+        hits = ms.find_motif(seq, off)
+        ms.close()
+        helpers.assert_same_hits(hits, ref, name)
+        assert len(ref) > 0, name

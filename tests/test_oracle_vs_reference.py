@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from rnamotif_b200 import fastn, oracle_port
+from oracle import oracle_port
+from rnamotif_b200 import fastn
 import helpers
 
 REF = helpers.REF

@@ -12,7 +12,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from rnamotif_b200 import fastn, gpumotif, oracle_port
+from oracle import oracle_port
+from rnamotif_b200 import fastn, gpumotif
 import helpers
 
 REF = helpers.REF

@@ -8,7 +8,8 @@ import sys
 import numpy as np
 import pytest
 
-from rnamotif_b200 import oracle_port, shard, synth
+from oracle import oracle_port
+from rnamotif_b200 import shard, synth
 import helpers
 
 
@@ -43,7 +44,8 @@ import os, sys, pickle
 import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
-from rnamotif_b200 import oracle_port, shard, synth
+from oracle import oracle_port
+from rnamotif_b200 import shard, synth
 import helpers
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
