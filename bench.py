@@ -434,6 +434,73 @@ def dominant_kernel(res, steps, n_descr):
     return name, ms, alg, share, k_sum / steps, (f_sum / steps if fl > 0 else None)
 
 
+def write_fasta(path, n_rec, rec_nt, seed, width=70):
+    """n_rec x rec_nt uniform acgt, `width` per line, ids syn%06d."""
+    rng = np.random.default_rng(seed)
+    lut = np.frombuffer(b"acgt", dtype=np.uint8)
+    full, rest = divmod(rec_nt, width)
+    with open(path, "wb") as fh:
+        for r in range(n_rec):
+            fh.write(b">syn%06d synthetic record %d\n" % (r, r))
+            a = np.empty((full, width + 1), dtype=np.uint8)
+            a[:, :width] = lut[rng.integers(0, 4, size=(full, width), dtype=np.uint8)]
+            a[:, width] = 10
+            a.tofile(fh)
+            if rest:
+                fh.write(lut[rng.integers(0, 4, size=rest, dtype=np.uint8)].tobytes() + b"\n")
+    return n_rec * rec_nt
+
+
+def binary_leg(descr, mnt, prefix_mnt):
+    """The drop-in program itself: rnamotif_b200/host/_build/rnamotif_gpu (the
+    reference's front end, score program and printer around libgpumotif) over a FASTA
+    FILE, wall clock from exec to exit, stdout to a file -- beside the reference binary
+    on a prefix of the same file, outputs compared byte for byte."""
+    exe = os.path.join(ROOT, "rnamotif_b200", "host", "_build", "rnamotif_gpu")
+    ref_bin = os.path.join(REF_DIR, "rnamotif")
+    dfile = os.path.join(REF_DIR, "data", DESCR_FILE.get(descr, os.path.join("test", descr + ".descr")))
+    if not (os.path.exists(exe) and os.path.exists(dfile)):
+        return {"unavailable": "rnamotif_gpu or the descriptor file was not built into this tree"}
+    strands = plan_strands(load_plan(descr))
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    env = dict(os.environ, EFNDATA=os.path.join(REF_DIR, "data", "efndata"), GPUMOTIF_STATS="1")
+    out = {}
+    with tempfile.TemporaryDirectory(dir=base) as tmp:
+        big, pre = os.path.join(tmp, "syn.fastn"), os.path.join(tmp, "prefix.fastn")
+        nt = write_fasta(big, mnt, 1_000_000, 1001)
+        write_fasta(pre, prefix_mnt, 1_000_000, 1001)  # same generator and seed: the first records of `big`
+        cwd = os.path.dirname(dfile)
+
+        def run(cmd, path, dest):
+            t0 = time.perf_counter()
+            with open(dest, "wb") as fh:
+                r = subprocess.run([cmd, "-descr", os.path.basename(dfile), path], cwd=cwd, env=env, stdout=fh,
+                                   stderr=subprocess.PIPE)
+            return time.perf_counter() - t0, r
+
+        run(exe, pre, os.path.join(tmp, "warm.out"))  # page cache, CUDA driver warm-up
+        dt, r = run(exe, big, os.path.join(tmp, "big.out"))
+        if r.returncode != 0:
+            return {"error": r.stderr.decode(errors="replace")[-400:]}
+        summary = [ln for ln in r.stderr.decode(errors="replace").splitlines() if "wall" in ln]
+        out.update(value=nt * strands / dt / 1e9, unit=UNIT, wall_s=dt, file_mnt=mnt,
+                   file_bytes=os.path.getsize(big), stdout_bytes=os.path.getsize(os.path.join(tmp, "big.out")),
+                   driver_summary=summary[-1] if summary else None,
+                   what="wall clock of `rnamotif_gpu -descr %s.descr FILE` from exec to exit (CUDA start-up, file read, "
+                        "search, score + print of every candidate, stdout to a file on tmpfs)" % descr)
+        dtg, rg = run(exe, pre, os.path.join(tmp, "pre_gpu.out"))
+        if os.path.exists(ref_bin):
+            dtr, rr = run(ref_bin, pre, os.path.join(tmp, "pre_ref.out"))
+            same = open(os.path.join(tmp, "pre_gpu.out"), "rb").read() == open(os.path.join(tmp, "pre_ref.out"), "rb").read()
+            out["prefix"] = {"mnt": prefix_mnt, "stdout_equal_reference": bool(same and rg.returncode == 0 and rr.returncode == 0),
+                             "stdout_bytes": os.path.getsize(os.path.join(tmp, "pre_ref.out")),
+                             "reference_wall_s": dtr, "rnamotif_gpu_wall_s": dtg,
+                             "reference_value": prefix_mnt * 1e6 * strands / dtr / 1e9}
+        else:
+            out["prefix"] = {"unavailable": "oracle/_ref/rnamotif did not travel"}
+    return out
+
+
 def run_gpu_arm(args):
     B = Bench(args)
     rank, world = B.rank, B.world
@@ -533,6 +600,10 @@ def run_gpu_arm(args):
             w, dt, kind = cpu_reference_run(args.descr, 1, 16, 1_000_000)
             line["cpu_baseline"] = {"value": w / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": "16 x 1 Mnt synthetic acgt, one process, default flags"}
+        if world == 1 and not args.no_binary:
+            line["binary"] = binary_leg(args.descr, args.binary_mnt, 8)
+            if line["binary"].get("prefix", {}).get("stdout_equal_reference") is False:
+                bad.append("rnamotif_gpu stdout")
         print(json.dumps(line), flush=True)
         if bad:
             print("bench.py: PARITY FAILED for " + ", ".join(bad), file=sys.stderr)
@@ -556,6 +627,8 @@ def main():
     ap.add_argument("--cfg-warmup", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle prefix checks")
+    ap.add_argument("--no-binary", action="store_true", help="skip the rnamotif_gpu program leg")
+    ap.add_argument("--binary-mnt", type=int, default=1024, help="Mnt of the FASTA file the program leg reads")
     ap.add_argument("--tile", type=int, default=0, help="starts per tile (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":

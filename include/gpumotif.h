@@ -85,6 +85,12 @@ int gm_plan_check(const gm_plan_t *plan);
  * counterpart in the reference (debugging aid, like its -d dump, src/rnamot.c:98). */
 int gm_plan_describe(const gm_plan_t *plan, char *out, size_t cap);
 
+/* Page-locked host memory (cudaMallocHost) for callers that are not linked against
+ * the CUDA runtime: uploads from such a buffer are asynchronous and run at full
+ * PCIe speed.  The reference reads into a malloc'ed sbuf (src/rnamot.c:143-149). */
+int gm_host_alloc(void **out, size_t n_bytes);
+void gm_host_free(void *p);
+
 /* Upload a batch of records given as the characters FN_fgetseq leaves in its
  * buffer (src/dbutil.c:42-128: letters only, any case, u or t): record r is
  * seq[rec_off[r] .. rec_off[r+1]).  The copy goes host -> device as is and is

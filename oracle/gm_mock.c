@@ -27,6 +27,8 @@ struct gm_ctx {
 	gm_plan_t plan;
 	char *seq;
 	int64_t *off;
+	int64_t *hdr;   /* gm_db_upload_fastn: text offset of every record's '>' */
+	char *wins;     /* gm_hit_windows */
 	int n_rec;
 	int64_t lo, hi;
 	int strands;
@@ -61,6 +63,8 @@ void gm_ctx_destroy(gm_ctx *c)
 		return;
 	free(c->seq);
 	free(c->off);
+	free(c->hdr);
+	free(c->wins);
 	free(c->hits);
 	free(c);
 }
@@ -79,6 +83,71 @@ int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n
 	c->n_rec = n_rec;
 	return 0;
 }
+
+/* FN_fgetseq (src/dbutil.c:42-128) as the two-state machine gm_fastn.cuh describes:
+ * outside a header every '>' starts a record and every isalpha character is kept;
+ * a header runs to its newline */
+int gm_db_upload_fastn(gm_ctx *c, const char *text, size_t n_bytes)
+{
+	size_t i, n_rec = 0, n_ch = 0, cap_rec = 1024;
+	int in_hdr = 0;
+	if (n_bytes > 0 && text[0] != '>') {
+		snprintf(mock_err, sizeof mock_err, "fastn text does not begin with '>'");
+		return -1;
+	}
+	free(c->seq);
+	free(c->off);
+	free(c->hdr);
+	c->seq = malloc(n_bytes + 1);
+	c->off = malloc((cap_rec + 1) * sizeof *c->off);
+	c->hdr = malloc((cap_rec + 1) * sizeof *c->hdr);
+	if (c->seq == NULL || c->off == NULL || c->hdr == NULL)
+		return -1;
+	for (i = 0; i < n_bytes; i++) {
+		const unsigned char ch = (unsigned char)text[i];
+		if (in_hdr) {
+			if (ch == '\n')
+				in_hdr = 0;
+		} else if (ch == '>') {
+			if (n_rec == cap_rec) {
+				cap_rec *= 2;
+				c->off = realloc(c->off, (cap_rec + 1) * sizeof *c->off);
+				c->hdr = realloc(c->hdr, (cap_rec + 1) * sizeof *c->hdr);
+				if (c->off == NULL || c->hdr == NULL)
+					return -1;
+			}
+			c->off[n_rec] = (int64_t)n_ch;
+			c->hdr[n_rec] = (int64_t)i;
+			n_rec++;
+			in_hdr = 1;
+		} else if ((ch >= 'a' && ch <= 'z') || (ch >= 'A' && ch <= 'Z'))
+			c->seq[n_ch++] = (char)ch;
+	}
+	c->off[n_rec] = (int64_t)n_ch;
+	c->hdr[n_rec] = (int64_t)n_bytes;
+	c->n_rec = (int)n_rec;
+	return 0;
+}
+
+int gm_db_records(const gm_ctx *c, const int64_t **rec_off, const int64_t **hdr_off, int *n_rec)
+{
+	if (rec_off)
+		*rec_off = c->off;
+	if (hdr_off)
+		*hdr_off = c->hdr;
+	if (n_rec)
+		*n_rec = c->n_rec;
+	return 0;
+}
+
+int64_t gm_db_total_nt(const gm_ctx *c) { return c->n_rec > 0 || c->off ? c->off[c->n_rec] : 0; }
+
+int gm_host_alloc(void **out, size_t n_bytes)
+{
+	*out = malloc(n_bytes ? n_bytes : 1);
+	return *out ? 0 : -1;
+}
+void gm_host_free(void *p) { free(p); }
 
 int gm_scan_launch(gm_ctx *c, int64_t g_begin, int64_t g_end, int strands)
 {
@@ -121,6 +190,44 @@ int gm_scan_finish(gm_ctx *c)
 		}
 	}
 	c->n = k;
+	return 0;
+}
+
+int gm_scan(gm_ctx *c, int64_t g_begin, int64_t g_end, int strands)
+{
+	return gm_scan_launch(c, g_begin, g_end, strands) || gm_scan_finish(c);
+}
+
+/* what fm_sbuf holds around every candidate: lower case, u -> t; on the complementary
+ * strand mk_rcmp's letters (src/rnamot.c:193-216); 0 outside the record */
+int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, size_t *stride)
+{
+	const int W = c->plan.dmaxlen < c->plan.windowsize ? c->plan.dmaxlen : c->plan.windowsize;
+	const size_t wlen = (size_t)((lead + W + trail + 1 + 7) & ~7);
+	size_t i, j;
+	free(c->wins);
+	c->wins = calloc(c->n ? c->n : 1, wlen);
+	if (c->wins == NULL)
+		return -1;
+	for (i = 0; i < c->n; i++) {
+		const gm_hit_hdr_t *h = (const gm_hit_hdr_t *)(c->hits + i * c->stride);
+		const int64_t slen = c->off[h->rec + 1] - c->off[h->rec];
+		const char *rec = c->seq + c->off[h->rec];
+		for (j = 0; j < wlen; j++) {
+			const int64_t p = (int64_t)h->szero - lead + (int64_t)j;
+			int ch;
+			if (p < 0 || p >= slen)
+				continue;
+			ch = (unsigned char)rec[h->comp ? slen - 1 - p : p] | 0x20;
+			if (ch == 'u')
+				ch = 't';
+			if (h->comp)
+				ch = ch == 'a' ? 't' : ch == 'c' ? 'g' : ch == 'g' ? 'c' : ch == 't' ? 'a' : 'n';
+			c->wins[i * wlen + j] = (char)ch;
+		}
+	}
+	*win = c->wins;
+	*stride = wlen;
 	return 0;
 }
 

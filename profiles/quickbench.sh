@@ -2,7 +2,7 @@
 # profiles/quickbench.sh TAG MNT descr... -- resident/e2e throughput per descriptor (no CPU leg)
 tag=$1; mnt=$2; shift 2
 for d in "$@"; do
-  python bench.py --descr "$d" --mnt $mnt --steps 3 --warmup 3 --no-cpu --configs none --no-parity > gpurun_out/qb_${tag}_$d.json 2> gpurun_out/qb_${tag}_$d.err
+  python bench.py --descr "$d" --mnt $mnt --steps 3 --warmup 3 --no-cpu --configs none --no-parity --no-binary > gpurun_out/qb_${tag}_$d.json 2> gpurun_out/qb_${tag}_$d.err
   python - "$d" gpurun_out/qb_${tag}_$d.json <<'PY'
 import json,sys
 try:

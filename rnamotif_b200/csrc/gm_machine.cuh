@@ -433,6 +433,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	uint32_t *ch_OK = ch_F + 4 * nwb;
 	const uint32_t *ch_F0 = ch_F; // the finished chain: bit p <=> the whole descriptor can be laid out from p
 	const bool deep = SIEVE && A.par.pf_deep != 0;
+	const bool TWO = MODE == 1 && SIEVE && A.par.sv_two != 0; // two-stage sieve (worklist path only)
 	const int sv_nws = ((TILE - 1) >> 5) + 2;               // sieve words per strand
 	const int sv_npass = (A.strands * sv_nws + 31) >> 5;
 
@@ -751,6 +752,46 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		return true;
 	};
 
+	// Stage 2 of the two-stage sieve (DevParams::sv_two), per start: the first helix's
+	// span-end test (wc_mask) and, for every span end and helix length that passes it,
+	// the look-ahead the word-parallel main pass applies per span offset -- the first
+	// interior helix can start behind the 5' strand (a bit of sv_K) and the last one
+	// can end before the 3' strand (tail_feasible).
+	auto accept2 = [&](int q) -> bool {
+		int comp, idx, slen, szero;
+		uint32_t rec;
+		if (!locate(q, comp, idx, rec, slen, szero))
+			return false;
+		const DevSearch &S0 = sm_ds[0];
+		const DevSearch &SP = sm_ds[A.par.pf_search];
+		const uint8_t *sq = comp ? sm_rc + (Lbytes - 1 - idx) : sm_fwd + idx;
+		const int base = comp ? Lbytes - 1 - idx : idx;
+		const int dl = min(W, slen - szero) - 1;
+		if (S0.rx5 >= 0 && S0.mm5 == 0 && !PV.regex[S0.rx5].eol &&
+		    !rx_match(PV.regex[S0.rx5], sq, min(S0.maxlen, dl + 1)))
+			return false;
+		const int pz = A.par.pf_z;
+		const int lsd = pz + SP.dlo;
+		const uint32_t *K = sv_K + comp * nwb;
+		for (int hi = min(dl, pz + SP.dhi); hi >= lsd; hi -= 64) {
+			const int l0 = max(lsd, hi - 63);
+			uint64_t v = wc_mask(pb, sq, comp, base, SP.dupi, SP.flt, pz, l0, hi - l0 + 1);
+			while (v) {
+				const int s3 = l0 + __ffsll((long long)v) - 1;
+				v &= v - 1;
+				for (int hl = SP.minlen; hl <= SP.maxlen; hl++) {
+					const int kp = base + pz + hl + SP.kid_off;
+					if (SP.kid_t >= 0 && !((K[kp >> 5] >> (kp & 31)) & 1u))
+						continue;
+					if (SP.lk_t >= 0 && !tail_feasible(pb, sq, comp, base, SP, sm_ds[SP.lk_t], pz, s3, hl))
+						continue;
+					return true;
+				}
+			}
+		}
+		return false;
+	};
+
 	// ---- composition chain (a sieve term) ----
 	// Going through the descriptor's elements from the last to the first, F(p) = "this
 	// element and everything behind it can be laid out contiguously from p, every
@@ -834,7 +875,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		const int nv = (int)(gB - gA);
 		for (int st = 0; st < A.strands; st++) {
 			const int zlo = (st ? Lbytes - H - nv : H) + A.par.pf_z, zhi = zlo + nv - 1; // helix starts of this tile
-			if (SP.lk_t >= 0) {
+			if (SP.lk_t >= 0 && !TWO) {
 				// ends asked about: zb + d - hl - lk_off; the helices that end there start
 				// up to maxglen - 1 earlier
 				const DevSearch &T = sm_ds[SP.lk_t];
@@ -908,7 +949,8 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				// ends asked about at span offset d: e0 + d + m, m = nhl-1-j for length minlen + j
 				const int e0 = (w_ << 5) - SP.minlen - SP.lk_off - (nhl - 1);
 				const bool has_lk = deep && SP.lk_t >= 0;
-				word = !A.par.sv_helix ? ~0u : sieve_word_main(pb, strand_, SP.dupi, SP.flt, w_, SP.dlo, SP.dhi,
+				word = !A.par.sv_helix ? ~0u : TWO ? (kh[0] | kh[1] | kh[2] | kh[3]) :
+					sieve_word_main(pb, strand_, SP.dupi, SP.flt, w_, SP.dlo, SP.dhi,
 					[&](int d, uint32_t f) -> uint32_t {
 						if (!has_lk)
 							return f & (kh[0] | kh[1] | kh[2] | kh[3]);
@@ -991,9 +1033,30 @@ __global__ void gm_search_kernel(const ScanArgs A)
 					chain_build();
 				if (deep)
 					sieve_aux();
+				int qhead = 0, qtail = 0; // two-stage sieve: stage-1 survivors, compacted (warp-uniform)
 				for (int pass_ = 0; pass_ < sv_npass; pass_++) {
 					int st_, w_;
 					uint32_t word = sieve_pass(pass_, st_, w_);
+					if (TWO) {
+						// stage 1 left its survivors in `word`: compact them into the warp's
+						// queue and run stage 2 on 32 of them at a time, one per lane
+						while (__ballot_sync(0xffffffffu, word != 0)) {
+							const bool has = word != 0;
+							const int q = has ? sieve_pop(word, st_, w_) : 0;
+							const unsigned pm = __ballot_sync(0xffffffffu, has);
+							if (has)
+								myq[(qtail + __popc(pm & ((1u << lane) - 1))) & (GM_QCAP - 1)] = (uint16_t)q;
+							qtail += __popc(pm);
+							__syncwarp();
+							while (qtail - qhead >= 32) {
+								const int q2 = myq[(qhead + lane) & (GM_QCAP - 1)];
+								qhead += 32;
+								__syncwarp();
+								wl_append(accept2(q2), q2, 0, 0);
+							}
+						}
+						continue;
+					}
 					while (__ballot_sync(0xffffffffu, word != 0)) {
 						int q = 0;
 						bool pass = false;
@@ -1003,6 +1066,11 @@ __global__ void gm_search_kernel(const ScanArgs A)
 						}
 						wl_append(pass, q, 0, 0);
 					}
+				}
+				if (qtail != qhead) {
+					const bool mine = lane < qtail - qhead;
+					const int q2 = mine ? myq[(qhead + lane) & (GM_QCAP - 1)] : 0;
+					wl_append(mine && accept2(q2), q2, 0, 0);
 				}
 			} else {
 				for (;;) {

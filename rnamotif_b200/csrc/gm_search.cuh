@@ -105,6 +105,10 @@ struct DevParams {
 	int sieve;              // level-0 sieve (sieve_word): word-parallel test of pf_search's span ends
 	int pf_deep;            // second stage behind the sieve: kid / tail look-ahead per span end
 	int sv_helix;           // the sieve has a helix term (pf_search); otherwise only the literal term
+	int sv_two;             // two-stage sieve: stage 1 = the look-ahead bitsets (first interior helix and
+	                        // its sibling), chain and literal terms as words; stage 2 = the first helix's
+	                        // span-end test per surviving START (wc_mask) -- cheaper than the word-parallel
+	                        // main pass when stage 1 leaves few starts
 	int sv_id;              // index in dups[] of the identity table (its bitsets are the base bitsets)
 	// Composition chain (a term of the level-0 sieve, chain_build in gm_machine.cuh): the
 	// descriptor's elements from last to first as steps (min, max, allowed bases,

@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -124,6 +125,21 @@ struct gm_ctx {
 extern "C" const char *gm_last_error(void) { return g_err; }
 extern "C" const char *gm_version(void) { return "libgpumotif 0.1 (sm_100a)"; }
 
+// pinned host memory for callers without the CUDA runtime (the C driver's text buffers)
+extern "C" int gm_host_alloc(void **out, size_t n_bytes)
+{
+	if (out == NULL)
+		return fail("out is NULL");
+	*out = NULL;
+	CU(cudaMallocHost(out, n_bytes ? n_bytes : 1));
+	return 0;
+}
+extern "C" void gm_host_free(void *p)
+{
+	if (p != NULL)
+		cudaFreeHost(p);
+}
+
 extern "C" int gm_device_count(void)
 {
 	int n = 0;
@@ -158,6 +174,11 @@ static search_kernel_t pre_kernel(int pf)
 {
 	return pf == 2 ? (search_kernel_t)gm_search_kernel<1, false, 2> : pf == 1 ? (search_kernel_t)gm_search_kernel<1, false, 1> : (search_kernel_t)gm_search_kernel<1, false, 0>;
 }
+
+// Dynamic shared memory every kernel is allowed to ask for.  The attribute belongs to
+// the KERNEL (per device), not to a context: two contexts whose plans pick the same
+// kernel with different needs would otherwise undo each other's setting.
+#define GM_SMEM_OPTIN (227 * 1024)
 
 // --------------------------------------------------------------- plan checks
 
@@ -603,6 +624,32 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 				par->pf_deep = 2;
 		}
 	}
+	// Two-stage sieve (DevParams::sv_two) when the look-ahead bitsets alone leave few
+	// starts: estimated density of "first interior helix and its sibling can form" from
+	// the share of pairs the table allows and the number of span offsets
+	par->sv_two = 0;
+	if (par->sieve && par->pf_deep && ds[par->pf_search].kid_t >= 0 && getenv("GPUMOTIF_NO_TWO_STAGE") == NULL) {
+		auto dens = [&](int t) {
+			const DevSearch &T = ds[t];
+			int allowed = 0;
+			for (int x = 0; x < 4; x++)
+				for (int y = 0; y < 4; y++)
+					allowed += (T.duplex >> (x * 5 + y)) & 1u;
+			const double q = allowed / 16.0;
+			const int req = T.flt & 0xff, budget = (T.flt >> 8) & 0xff;
+			double p = pow(q, req);
+			if (budget >= 1)
+				p += req * (1 - q) * pow(q, req - 1);
+			return std::min(1.0, (T.dhi - T.dlo + 1) * p);
+		};
+		const DevSearch &SP = ds[par->pf_search];
+		double d1 = dens(SP.kid_t);
+		if (par->pf_deep == 2)
+			d1 *= dens(ds[SP.kid_t].sib_t);
+		d1 *= SP.maxlen - SP.minlen + 1;
+		if (d1 < 0.12 || getenv("GPUMOTIF_TWO_STAGE") != NULL)
+			par->sv_two = 1;
+	}
 	// a literal alone also makes a sieve (its occurrence bitset, ORed over the window)
 	if (!par->sieve && par->lit_present && par->lit_lmax - par->lit_lmin <= 256 && getenv("GPUMOTIF_NO_SIEVE") == NULL)
 		par->sieve = 1;
@@ -766,8 +813,8 @@ extern "C" int gm_plan_describe(const gm_plan_t *plan, char *out, size_t cap)
 	};
 	static const char *kn[] = {"ss", "wc", "pk", "ph", "tr", "qu"};
 	put("window %d halo %d lite %d n_dups %d refill %d\n", par.w_winsize, par.halo, par.lite, par.n_dups, par.refill_min);
-	put("level0: pf_search %d pf_z %d sieve %d helix-term %d deep %d literal %d (len %d at %d..%d mm %d) chain %d\n", par.pf_search,
-	    par.pf_z, par.sieve, par.sv_helix, par.pf_deep, par.lit_present, par.lit_len, par.lit_lmin, par.lit_lmax, par.lit_mm,
+	put("level0: pf_search %d pf_z %d sieve %d two-stage %d helix-term %d deep %d literal %d (len %d at %d..%d mm %d) chain %d\n", par.pf_search,
+	    par.pf_z, par.sieve, par.sv_two, par.sv_helix, par.pf_deep, par.lit_present, par.lit_len, par.lit_lmin, par.lit_lmax, par.lit_mm,
 	    par.chain);
 	for (int s = 0; s < par.n_searches; s++) {
 		const DevSearch &S = ds[s];
@@ -825,7 +872,7 @@ static int warps_per_sm(gm_ctx *c, int threads, int tile)
 	if (need + 1024 > 227 * 1024)
 		return 0;
 	int n = 0;
-	if (cudaFuncSetAttribute(fused_kernel(c->full, pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
+	if (cudaFuncSetAttribute(fused_kernel(c->full, pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN) != cudaSuccess ||
 	    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_kernel(c->full, pf_of(c->par)), threads, need) != cudaSuccess) {
 		cudaGetLastError();
 		return 0;
@@ -879,7 +926,7 @@ static int configure_launch(gm_ctx *c, int tile)
 	c->threads = best_t;
 	c->par.tile = tile;
 	c->smem_bytes = smem_need(c, best_t, tile);
-	CU(cudaFuncSetAttribute(fused_kernel(c->full, pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+	CU(cudaFuncSetAttribute(fused_kernel(c->full, pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN));
 	int per_sm = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel(c->full, pf_of(c->par)), c->threads, c->smem_bytes));
 	if (per_sm < 1)
@@ -940,7 +987,7 @@ static int configure_launch(gm_ctx *c, int tile)
 			if (need > smem_sm)
 				continue;
 			int n = 0;
-			if (cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) != cudaSuccess ||
+			if (cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN) != cudaSuccess ||
 			    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dfs_kernel(c->full), t, need) != cudaSuccess)
 				continue;
 			if (n * t > best_w) {
@@ -953,8 +1000,8 @@ static int configure_launch(gm_ctx *c, int tile)
 		cudaGetLastError();
 		int na = 0;
 		if (c->b_threads > 0 && c->a_smem <= smem_sm &&
-		    cudaFuncSetAttribute(pre_kernel(pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->a_smem) == cudaSuccess &&
-		    cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->b_smem) == cudaSuccess &&
+		    cudaFuncSetAttribute(pre_kernel(pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN) == cudaSuccess &&
+		    cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN) == cudaSuccess &&
 		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(pf_of(c->par)), c->a_threads, c->a_smem) == cudaSuccess &&
 		    na >= 1) {
 			c->a_blocks = na * c->n_sm;

@@ -34,7 +34,7 @@ class GpuMotifError(RuntimeError):
 
 _lib = None
 
-EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_ctx_create", "gm_ctx_destroy",
+EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_host_alloc", "gm_host_free", "gm_ctx_create", "gm_ctx_destroy",
            "gm_plan_check", "gm_plan_describe", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
            "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",

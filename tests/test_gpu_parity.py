@@ -241,11 +241,12 @@ def test_setters_refuse_while_a_scan_is_in_flight():
 def test_hit_dense_input_and_long_windows():
     """Descriptors of the reference's corpus whose candidate volume or window kept
     them out of the committed goldens (tests/golden/manifest.json), on inputs small
-    enough for the oracle: mpr (mispair-tolerant hairpin: tens of candidates per
-    hundred nucleotides), hlx.gf.iu / phlx.pfrac (unbounded interior: the window is
-    the 6000-nt default), eloop."""
+    enough for the oracle: mpr / phlx.pfrac (mispair-tolerant hairpins: more than one
+    candidate per nucleotide), hlx.gf.iu (1000-nt loops: 50 candidates per
+    nucleotide), pk.gf.iu (pseudoknot with three 1000-nt single strands: 10^5
+    candidates from a few hundred nucleotides), eloop (the 6000-nt default window)."""
     for name, n in (("descr.mpr", 6000), ("descr.hlx.gf.iu", 9000), ("descr.phlx.pfrac", 9000),
-                    ("descr.pk.gf.iu", 7000), ("descr.eloop", 9000)):
+                    ("descr.pk.gf.iu", 400), ("descr.eloop", 8000)):
         plan = helpers.load_extra_plan(name)
         if plan is None:
             pytest.skip("plan of %s not committed" % name)
