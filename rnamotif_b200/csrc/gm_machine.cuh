@@ -386,7 +386,7 @@ __device__ __noinline__ bool probes_ok(const Lane &L, const DevSearch &S, int s5
 // word-parallel sieve (sieve_word).  A template parameter so that each plan
 // runs only the code it needs (the kernel is instruction-cache bound).
 template <int MODE, bool FULL, int PF>
-__global__ void gm_search_kernel(const ScanArgs A)
+__global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) gm_search_kernel(const ScanArgs A)
 {
 	constexpr bool SIEVE = PF == 2; // word-parallel level-0 sieve instead of the per-start prefilter
 	// literal prefilter: per start (PF == 1) or as one more term of the sieve
@@ -434,6 +434,10 @@ __global__ void gm_search_kernel(const ScanArgs A)
 	const uint32_t *ch_F0 = ch_F; // the finished chain: bit p <=> the whole descriptor can be laid out from p
 	const bool deep = SIEVE && A.par.pf_deep != 0;
 	const bool TWO = MODE == 1 && SIEVE && A.par.sv_two != 0; // two-stage sieve (worklist path only)
+	// per-start stage behind the sieve words (accept2): always in two-stage mode, and when
+	// the first helix has probes (seq= of single strands at a place the helix fixes)
+	const bool ST2 = TWO || (MODE == 1 && SIEVE && A.par.sv_helix != 0 && A.par.pf_search >= 0 &&
+		A.ds[max(A.par.pf_search, 0)].n_probe > 0);
 	const int sv_nws = ((TILE - 1) >> 5) + 2;               // sieve words per strand
 	const int sv_npass = (A.strands * sv_nws + 31) >> 5;
 
@@ -773,6 +777,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 		const int pz = A.par.pf_z;
 		const int lsd = pz + SP.dlo;
 		const uint32_t *K = sv_K + comp * nwb;
+		const bool use_k = deep && SP.kid_t >= 0;
 		for (int hi = min(dl, pz + SP.dhi); hi >= lsd; hi -= 64) {
 			const int l0 = max(lsd, hi - 63);
 			uint64_t v = wc_mask(pb, sq, comp, base, SP.dupi, SP.flt, pz, l0, hi - l0 + 1);
@@ -781,10 +786,16 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				v &= v - 1;
 				for (int hl = SP.minlen; hl <= SP.maxlen; hl++) {
 					const int kp = base + pz + hl + SP.kid_off;
-					if (SP.kid_t >= 0 && !((K[kp >> 5] >> (kp & 31)) & 1u))
+					if (use_k && !((K[kp >> 5] >> (kp & 31)) & 1u))
 						continue;
 					if (SP.lk_t >= 0 && !tail_feasible(pb, sq, comp, base, SP, sm_ds[SP.lk_t], pz, s3, hl))
 						continue;
+					if (SP.n_probe) {
+						Lane Lq = L;
+						Lq.sq = sq;
+						if (!probes_ok(Lq, SP, pz, s3, hl, dl))
+							continue;
+					}
 					return true;
 				}
 			}
@@ -1037,7 +1048,7 @@ __global__ void gm_search_kernel(const ScanArgs A)
 				for (int pass_ = 0; pass_ < sv_npass; pass_++) {
 					int st_, w_;
 					uint32_t word = sieve_pass(pass_, st_, w_);
-					if (TWO) {
+					if (ST2) {
 						// stage 1 left its survivors in `word`: compact them into the warp's
 						// queue and run stage 2 on 32 of them at a time, one per lane
 						while (__ballot_sync(0xffffffffu, word != 0)) {

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h> // header-only: ranges cost nothing unless a profiler is attached
 
 #include "gpumotif.h"
 #include "gm_machine.cuh"
@@ -44,6 +45,12 @@ static int fail(const char *fmt, ...)
 		if (e_ != cudaSuccess)                                                          \
 			return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while (0)
+
+// NVTX range over a scope (upload / scan launch / wait / ordering / gather / windows)
+struct NvtxRange {
+	explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+};
 
 struct gm_ctx {
 	gm_plan_t plan;
@@ -1234,6 +1241,7 @@ static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
 // record chunk_ev[i].  Returns without waiting.
 static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src, bool mark_start = true)
 {
+	NvtxRange nvtx_("gpumotif: upload chunks (H2D + pack)");
 	const int64_t n = c->total_nt;
 	const size_t pbytes = (size_t)(((n + 15) / 16) * 8) + 1024; // slack: kernels read whole 16-byte groups past the end
 	if (ensure((void **)&c->d_packed, &c->packed_cap, pbytes))
@@ -1327,6 +1335,7 @@ extern "C" int gm_db_upload_fastn(gm_ctx *c, const char *text, size_t n_bytes)
 		return fail("text too long");
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->copy_stream));
+	NvtxRange nvtx_("gpumotif: upload fastn (H2D + device reader)");
 	if (n_bytes > 0 && text[0] != '>')
 		return fail("fastn text does not begin with '>' (src/dbutil.c:56-60)");
 	const int64_t n = (int64_t)n_bytes;
@@ -1430,6 +1439,7 @@ extern "C" int64_t gm_db_total_nt(const gm_ctx *c) { return c ? c->total_nt : -1
 
 static int launch(gm_ctx *c)
 {
+	NvtxRange nvtx_("gpumotif: launch sieve / enumeration kernels");
 	if (c->d_hits == NULL) {
 		CU(cudaMalloc(&c->d_hits, c->hit_cap * (size_t)c->stride_words * 4));
 	}
@@ -1636,6 +1646,8 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	c->pending = false;
 	CU(cudaSetDevice(c->device));
 	unsigned long long cnt[8];
+	nvtxRangePushA("gpumotif: wait for the kernels");
+	struct PopOnce { bool done = false; void pop() { if (!done) { nvtxRangePop(); done = true; } } ~PopOnce() { pop(); } } wait_range;
 	for (;;) {
 		CU(cudaMemcpyAsync(cnt, c->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
@@ -1690,6 +1702,8 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 		if (launch(c))
 			return -1;
 	}
+	wait_range.pop();
+	NvtxRange nvtx_("gpumotif: order + gather candidates");
 	const size_t n = (size_t)cnt[1];
 	const size_t sw = (size_t)c->stride_words;
 	if (n * sw > c->h_raw_cap) {
@@ -1826,6 +1840,7 @@ extern "C" int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, 
 	if (c->d_seq_chars == NULL)
 		return fail("no database uploaded");
 	CU(cudaSetDevice(c->device));
+	NvtxRange nvtx_("gpumotif: hit windows");
 	const int wlen = (lead + c->par.w_winsize + trail + 1 + 7) & ~7;
 	const size_t n = c->n_hits;
 	const size_t bytes = n * (size_t)wlen;

@@ -98,6 +98,7 @@ static int devices[MAX_GPUS], n_gpus;
 static int64_t batch_nt = 128ll << 20;
 static int ctx_lead, ctx_trail; /* characters the sink's tail may read before / behind a window */
 static double t_read, t_search, t_replay; /* GPUMOTIF_STATS summary */
+static double t_setup, t_loop, t_down;
 static uint64_t tot_nt, tot_hits;
 
 /* ------------------------------------------------------------------ replay of one batch
@@ -716,6 +717,7 @@ int main(int argc, char *argv[])
 	ctx_lead = plan.lctx.present ? plan.lctx.maxlen : 0;
 	ctx_trail = plan.rctx.present ? 2 * plan.rctx.maxlen : 0;
 
+	t_setup = now_s() - t_start; /* front end + plan */
 	if (RM_fm_init())
 		exit(1);
 	RM_setprog(P_BEGIN);
@@ -732,7 +734,12 @@ int main(int argc, char *argv[])
 			if (gm_ctx_create(&slots[i].ctx, &plan, slots[i].device))
 				die_gm("gm_ctx_create");
 		}
-		ecnt = run_pipeline(&bail_file, &bail_off);
+		{
+			const double t0 = now_s();
+			t_setup = t0 - t_start; /* ... + contexts */
+			ecnt = run_pipeline(&bail_file, &bail_off);
+			t_loop = now_s() - t0;
+		}
 		if (bail_file >= 0) {
 			/* hand over to the host reader at the batch the pipeline stopped at */
 			rm_args->a_c_dbfname = bail_file;
@@ -745,9 +752,13 @@ int main(int argc, char *argv[])
 			if (rm_dbfp != NULL)
 				run_host_reader(slots[0].ctx, ecnt);
 		}
-		for (i = 0; i < n_slots; i++) {
-			gm_ctx_destroy(slots[i].ctx);
-			gm_host_free(slots[i].text);
+		{
+			const double t0 = now_s();
+			for (i = 0; i < n_slots; i++) {
+				gm_ctx_destroy(slots[i].ctx);
+				gm_host_free(slots[i].text);
+			}
+			t_down = now_s() - t0;
 		}
 	} else {
 		gm_ctx *ctx;
@@ -766,9 +777,10 @@ int main(int argc, char *argv[])
 		const double wall = now_s() - t_start;
 		const double snt = (double)tot_nt * (chk_both_strs ? 2 : 1);
 		fprintf(stderr, "rnamotif_gpu: %llu nt, %llu candidates replayed, %d gpu(s), wall %.3f s "
-			"(%.2f G strand-nt/s); replay %.3f s, replay waiting for batches %.3f s, host reader %.3f s\n",
-			(unsigned long long)tot_nt, (unsigned long long)tot_hits, n_gpus, wall, snt / wall / 1e9, t_replay,
-			t_search, t_read);
+			"(%.2f G strand-nt/s): set-up %.3f s, pipeline %.3f s (%.2f G strand-nt/s; replay %.3f s, replay waiting "
+			"for batches %.3f s), tear-down %.3f s, host reader %.3f s\n",
+			(unsigned long long)tot_nt, (unsigned long long)tot_hits, n_gpus, wall, snt / wall / 1e9, t_setup, t_loop,
+			t_loop > 0 ? snt / t_loop / 1e9 : 0.0, t_replay, t_search, t_down, t_read);
 	}
 	(void)g;
 	exit(0);

@@ -39,7 +39,6 @@ def run(binary, name, extra_env=None):
 @pytest.mark.parametrize("name", sorted(MD5))
 def test_make_test_stdout_md5(name):
     out = run(GPU_BIN, name)
-    assert out.count(b"\n>") + out.startswith(b">") >= 0
     assert hashlib.md5(out).hexdigest() == MD5[name]["md5"], f"{name}: stdout differs from the reference"
 
 
@@ -79,3 +78,19 @@ def test_prune_option_equals_rnamotif_piped_through_rmprune(name):
     want = subprocess.run([PRUNE_BIN], input=ref, capture_output=True, timeout=600, check=True).stdout
     got = run(GPU_BIN, name, {"GPUMOTIF_PRUNE": "1"})
     assert got == want
+
+
+RMFMT = os.path.join(helpers.REF, "rmfmt")
+
+
+@pytest.mark.skipif(not (have and os.path.exists(RMFMT)), reason="oracle/_ref (rmfmt, test data) or rnamotif_gpu not built")
+@pytest.mark.parametrize("name", sorted(MD5))
+def test_make_test_chk_goldens(name):
+    """The reference's own `make test` (test/Makefile:30-245): rnamotif ... | rmfmt -l
+    diffed against test/<name>.chk -- with rnamotif_gpu in rnamotif's place and the
+    reference's rmfmt and .chk files as they are."""
+    out = run(GPU_BIN, name)
+    fmt = subprocess.run([RMFMT, "-l"], input=out, capture_output=True, timeout=600, cwd=os.path.join(DATA, "test"))
+    assert fmt.returncode == 0, fmt.stderr.decode(errors="replace")[-500:]
+    with open(os.path.join(DATA, "test", name + ".chk"), "rb") as fh:
+        assert fmt.stdout == fh.read(), f"{name}: differs from the reference's {name}.chk"
