@@ -76,6 +76,16 @@ def load_plan(name):
         return fh.read()
 
 
+def load_score(name):
+    """The descriptor's MAIN score program for the device's pre-screen (gm_ctx_set_score), or None."""
+    path = os.path.join(PLAN_DIR, name + ".score.gz")
+    if not os.path.exists(path):
+        return None
+    with gzip.open(path, "rb") as fh:
+        sc = fh.read()
+    return sc if int(np.frombuffer(sc, dtype=np.int32, count=1)[0]) else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -271,7 +281,7 @@ class Bench:
         return bool(t.item())
 
     # --------------------------------------------------------------------------------
-    def measure(self, plan, rec_off, total, steps, warmup, clocks=False, prefix_recs=0, tile=0):
+    def measure(self, plan, rec_off, total, steps, warmup, clocks=False, prefix_recs=0, tile=0, score=None):
         """Resident and end-to-end throughput of one plan over the database in the
         shared buffers; parity checks outside the timed regions.  Returns a dict."""
         from rnamotif_b200 import gpumotif
@@ -280,12 +290,15 @@ class Bench:
         ms = gpumotif.MotifSearch(plan, device=self.local)
         if tile:
             ms.set_tile(tile)
+        if score is not None:
+            ms.set_score(score)  # candidates the score section rejects outright are dropped at the sink
         stream = torch.cuda.ExternalStream(ms.stream, device=torch.device("cuda", self.local))
         res = {"strands": strands, "n_descr": ms.n_descr}
 
         # ---- resident leg -----------------------------------------------------
         ms.set_device_chars(self.d_chars.data_ptr(), rec_off)
-        acc = {"kernel_ms": [], "filter_ms": [], "launches": 0, "filter_launches": 0, "survivors": 0, "hits": 0}
+        acc = {"kernel_ms": [], "filter_ms": [], "launches": 0, "filter_launches": 0, "survivors": 0, "hits": 0,
+               "score_rejected": 0}
 
         def step_resident():
             ms.scan(0, total, strands, copy=False)
@@ -296,6 +309,7 @@ class Bench:
             acc["filter_launches"] += st.n_filter_launches
             acc["survivors"] = st.n_survivors
             acc["hits"] = st.n_hits
+            acc["score_rejected"] = st.n_score_rejected
 
         for _ in range(warmup):
             step_resident()
@@ -346,6 +360,8 @@ class Bench:
         finally:
             del os.environ["GPUMOTIF_SEG_NT"]
         ms2.set_tile(416)
+        if score is not None:
+            ms2.set_score(score)
         ms2.set_device_chars(self.d_chars.data_ptr(), rec_off)
         hits_alt = ms2.scan(0, total, strands, copy=True)
         same = same and len(hits_alt) == len(hits_res) and hits_alt.tobytes() == hits_res.tobytes()
@@ -353,6 +369,7 @@ class Bench:
         if prefix_recs > 0 and self.rank == 0:
             n_pre = min(prefix_recs, len(rec_off) - 1)
             pre_nt = int(rec_off[n_pre])
+            ms2.set_score(None)  # the oracle enumerates every candidate
             hits_pre = ms2.scan(0, pre_nt, strands, copy=True)
             ok, n_ref, W = oracle_check(plan, self.h_chars[:pre_nt].numpy(), rec_off[:n_pre + 1], strands, hits_pre)
             par.update(prefix_nt=pre_nt, prefix_candidates=int(n_ref), prefix_equal_oracle=bool(ok))
@@ -565,7 +582,7 @@ def run_gpu_arm(args):
         cplan = load_plan(pname)
         c_off, c_total = B.database(lengths, seed)
         r = B.measure(cplan, c_off, c_total, args.cfg_steps, args.cfg_warmup,
-                      prefix_recs=(pre if not args.no_parity else 0))
+                      prefix_recs=(pre if not args.no_parity else 0), score=load_score(pname))
         if rank != 0:
             continue
         kname, kms, kalg, kshare, kk_ms, kf_ms = dominant_kernel(r, args.cfg_steps, r["n_descr"])
@@ -577,6 +594,8 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": r["d2h"]},
             "steps": args.cfg_steps, "warmup": args.cfg_warmup,
             "candidates_per_step_rank0": r["candidates"], "survivors_of_level0_rank0": int(r["acc"]["survivors"]),
+            "score_prescreen": ({"on": True, "rejected_on_device_per_step_rank0": int(r["acc"].get("score_rejected", 0))}
+                                if load_score(pname) is not None else {"on": False}),
             "kernel": kname, "kernel_ms": kms, "kernel_share_of_step": kshare,
             "kernels_ms_per_step": kk_ms, "filter_ms_per_step": kf_ms,
             "hbm_frac": kalg / (kms / 1e3) / 1e9 / pk["hbm_gbs"],

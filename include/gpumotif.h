@@ -38,6 +38,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "gpumotif_plan.h"
+#include "gpumotif_score.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -62,6 +63,7 @@ typedef struct gm_scan_stats {
 	uint64_t n_survivors;    /* starts it handed to the enumeration kernel */
 	uint32_t n_filter_launches;
 	uint32_t pad_;
+	uint64_t n_score_rejected; /* candidates the score pre-screen dropped at the sink (gm_ctx_set_score) */
 } gm_scan_stats_t;
 
 const char *gm_last_error(void);
@@ -202,6 +204,21 @@ int gm_prune_hits(const gm_plan_t *plan, const void *hits, size_t n, size_t stri
  */
 int gm_order_hits(const void *hits, size_t n, size_t stride, int n_descr, const double *score,
                   const int32_t *name_rank, const int64_t *rec_off, int n_rec, uint32_t *perm);
+
+/*
+ * Score-section pre-screen (include/gpumotif_score.h): hand the
+ * context the flattened MAIN score program and the hit sink runs it on every
+ * candidate and drops the ones it REJECTs -- they never reach gm_hits(), so the
+ * caller's RM_score / print_match replay (src/find_motif.c:373-392) sees only
+ * candidates the program would not reject outright.  score = NULL (or
+ * score->present = 0) switches it off.  gm_scan_stats_t::n_score_rejected counts
+ * the dropped candidates of a scan.
+ * gm_score_prescreen is the same interpreter on the host over one hit record (1 =
+ * the program rejects it; `sbuf` = the searched strand as fm_sbuf holds it, slen its
+ * length): the CPU check of the device's decision.
+ */
+int gm_ctx_set_score(gm_ctx *c, const gm_score_t *score);
+int gm_score_prescreen(const gm_plan_t *plan, const gm_score_t *score, const void *hit, const char *sbuf, int slen);
 
 /* Tunables (before the first scan): hit-buffer capacity in records (default
  * 1<<20; grown automatically when a scan overflows), starts per tile. */

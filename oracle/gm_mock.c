@@ -34,6 +34,8 @@ struct gm_ctx {
 	int strands;
 	char *hits;
 	size_t n, stride;
+	gm_score_t *score;  /* gm_ctx_set_score: candidates it rejects are dropped like the device does */
+	uint64_t n_rejected;
 };
 
 static char mock_err[512] = "";
@@ -66,7 +68,21 @@ void gm_ctx_destroy(gm_ctx *c)
 	free(c->hdr);
 	free(c->wins);
 	free(c->hits);
+	free(c->score);
 	free(c);
+}
+
+int gm_ctx_set_score(gm_ctx *c, const gm_score_t *score)
+{
+	free(c->score);
+	c->score = NULL;
+	if (score != NULL && score->present) {
+		c->score = malloc(sizeof *score);
+		if (c->score == NULL)
+			return -1;
+		*c->score = *score;
+	}
+	return 0;
 }
 
 int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec)
@@ -163,6 +179,7 @@ int gm_scan_finish(gm_ctx *c)
 {
 	size_t cap = 1 << 16, i, k = 0;
 	int64_t n;
+	c->n_rejected = 0;
 	gmo_stats_t st;
 	for (;;) {
 		free(c->hits);
@@ -183,6 +200,29 @@ int gm_scan_finish(gm_ctx *c)
 		const gm_hit_hdr_t *h = (const gm_hit_hdr_t *)(c->hits + i * c->stride);
 		const int64_t slen = c->off[h->rec + 1] - c->off[h->rec];
 		const int64_t g = c->off[h->rec] + (h->comp ? slen - 1 - (int64_t)h->szero : (int64_t)h->szero);
+		if (g >= c->lo && g < c->hi && c->score != NULL) {
+			/* the searched strand of this record as fm_sbuf holds it */
+			char *sb = malloc((size_t)slen + 1);
+			int64_t p;
+			int rej;
+			if (sb == NULL)
+				return -1;
+			for (p = 0; p < slen; p++) {
+				int ch = (unsigned char)c->seq[c->off[h->rec] + (h->comp ? slen - 1 - p : p)] | 0x20;
+				if (ch == 'u')
+					ch = 't';
+				if (h->comp)
+					ch = ch == 'a' ? 't' : ch == 'c' ? 'g' : ch == 'g' ? 'c' : ch == 't' ? 'a' : 'n';
+				sb[p] = (char)ch;
+			}
+			sb[slen] = 0;
+			rej = gm_score_prescreen(&c->plan, c->score, h, sb, (int)slen);
+			free(sb);
+			if (rej) {
+				c->n_rejected++;
+				continue;
+			}
+		}
 		if (g >= c->lo && g < c->hi) {
 			if (k != i)
 				memmove(c->hits + k * c->stride, c->hits + i * c->stride, c->stride);
@@ -243,5 +283,6 @@ int gm_stats(const gm_ctx *c, gm_scan_stats_t *out)
 {
 	memset(out, 0, sizeof *out);
 	out->n_hits = c->n;
+	out->n_score_rejected = c->n_rejected;
 	return 0;
 }

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gm_search.cuh"
+#include "gm_score.h"
 
 namespace gm {
 
@@ -26,6 +27,8 @@ namespace gm {
 
 struct ScanArgs {
 	DevParams par;              // launch parameters (by value: they belong to this launch)
+	const gm_score_t *score;    // the score program's pre-screen (gm_ctx_set_score) or NULL
+	unsigned long long *score_rejected;
 	const gm_plan_t *plan;      // the context's own device copy of the plan ...
 	const DevSearch *ds;        // ... and of the derived per-search table
 	const uint8_t *packed;      // 4-bit codes, nucleotide g in byte g>>1, nibble g&1
@@ -409,7 +412,69 @@ __device__ __noinline__ bool sink_sites(const Lane &L)
 // then written by the whole warp at the next converged point of the machine loop
 // (sink_write: lane d formats element d), because a record is 8 + 2 n_descr words and
 // candidates can be frequent (trna.general: two per thousand strand-nt).
-__device__ __noinline__ bool sink_pass(Lane &L, int ctx[4])
+// mispair / mismatch counts of element d as the sink reports them
+__device__ __forceinline__ void el_counts(const Lane &L, int d, int &mpr, int &mm)
+{
+	if (PV.par.lite) {
+		// counts live in the frames: a helix head keeps its mispairs, an ss its mismatches
+		const int f1 = lo16(L_FR(L, PV.par.elsrc[d], 1));
+		if (PV.elems[d].type == GM_SS) {
+			mpr = 0;
+			mm = f1;
+		} else {
+			mpr = f1 & 0xff;
+			mm = 0;
+		}
+	} else {
+		const uint32_t em = L_EM(L, d);
+		mpr = lo16(em);
+		mm = hi16(em);
+	}
+}
+
+// The candidate a lane holds, as the score program's pre-screen reads it (gm_score.h).
+// Characters come from the lane's window: `lo`..`hi` are the window-relative
+// positions it covers; IUPAC code 0 (a letter outside the nucleotide codes) is
+// reported as unknown.
+struct ScoreEnv {
+	const Lane &L;
+	int lo, hi;
+	__device__ int ch(int pos) const
+	{
+		const int rel = pos - L.szero;
+		if (rel < lo || rel >= hi || pos < 0 || pos >= L.slen)
+			return -1;
+		const int code = icode_of(L.sq[rel]);
+		return code ? (int)"?acmgrsvtwyhkdbn"[code] : -1;
+	}
+	__device__ int off(int d) const { return L.szero + m_off(L, d); }
+	__device__ int len(int d) const { return m_len(L, d); }
+	__device__ int mpr(int d) const { int a, b; el_counts(L, d, a, b); return (int8_t)a; }
+	__device__ int mm(int d) const { int a, b; el_counts(L, d, a, b); return (int8_t)b; }
+	__device__ int comp() const { return L.comp; }
+	__device__ int pos() const { return L.comp ? L.slen - off(0) : off(0) + 1; }
+	__device__ int mlen() const
+	{
+		int n = 0;
+		for (int d = 0; d < L.ND; d++)
+			n += m_len(L, d);
+		return n;
+	}
+	__device__ int slen() const { return L.slen; }
+	__device__ const gm_elem_t &elem(int d) const { return PV.elems[d]; }
+	__device__ const gm_pairset_t &pairset(int i) const { return PV.pairsets[i]; }
+};
+
+__device__ __noinline__ bool sink_score(const Lane &L, const ScanArgs &A, int win_lo, int win_hi)
+{
+	ScoreEnv env = {L, win_lo, win_hi};
+	if (score_eval(*A.score, env) != SC_REJECT)
+		return true;
+	atomicAdd(A.score_rejected, 1ull);
+	return false;
+}
+
+__device__ __noinline__ bool sink_pass(Lane &L, const ScanArgs &A, int win_lo, int win_hi, int ctx[4])
 {
 	ctx[0] = ctx[1] = ctx[2] = ctx[3] = -1;
 	if (PV.par.strict_helices && !sink_strict(L))
@@ -417,6 +482,9 @@ __device__ __noinline__ bool sink_pass(Lane &L, int ctx[4])
 	if ((PV.lctx.present || PV.rctx.present) && !sink_context(L, ctx))
 		return false;
 	if (PV.n_sites > 0 && !sink_sites(L))
+		return false;
+	// the score program's outright rejections (gm_ctx_set_score)
+	if (A.score != NULL && !sink_score(L, A, win_lo, win_hi))
 		return false;
 	return true;
 }
@@ -436,21 +504,7 @@ __device__ __forceinline__ void sink_write(const Lane &Ls, const ScanArgs &A, in
 	for (int d = lane; d < Ls.ND; d += 32) {
 		const uint32_t el = el_word(Ls, d, lite);
 		int mpr, mm;
-		if (lite) {
-			// counts live in the frames: a helix head keeps its mispairs, an ss its mismatches
-			const int f1 = lo16(L_FR(Ls, PV.par.elsrc[d], 1));
-			if (PV.elems[d].type == GM_SS) {
-				mpr = 0;
-				mm = f1;
-			} else {
-				mpr = f1 & 0xff;
-				mm = 0;
-			}
-		} else {
-			const uint32_t em = L_EM(Ls, d);
-			mpr = lo16(em);
-			mm = hi16(em);
-		}
+		el_counts(Ls, d, mpr, mm);
 		h[8 + 2 * d] = (uint32_t)(szero + lo16(el));
 		h[9 + 2 * d] = (uint32_t)(hi16(el) & 0xffff) | ((uint32_t)(mpr & 0xff) << 16) |
 			((uint32_t)(mm & 0xff) << 24);

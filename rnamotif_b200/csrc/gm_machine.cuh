@@ -388,7 +388,7 @@ __device__ __noinline__ bool probes_ok(const Lane &L, const DevSearch &S, int s5
 template <int MODE, bool FULL, int PF>
 __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) gm_search_kernel(const ScanArgs A)
 {
-	constexpr bool SIEVE = PF == 2; // word-parallel level-0 sieve instead of the per-start prefilter
+	constexpr bool SIEVE = PF >= 2; // word-parallel level-0 sieve instead of the per-start prefilter (3: two-stage)
 	// literal prefilter: per start (PF == 1) or as one more term of the sieve
 	const bool LIT = PF == 1 || (SIEVE && A.par.lit_present != 0);
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) gm_search_kernel(const
 	uint32_t *ch_OK = ch_F + 4 * nwb;
 	const uint32_t *ch_F0 = ch_F; // the finished chain: bit p <=> the whole descriptor can be laid out from p
 	const bool deep = SIEVE && A.par.pf_deep != 0;
-	const bool TWO = MODE == 1 && SIEVE && A.par.sv_two != 0; // two-stage sieve (worklist path only)
+	constexpr bool TWO = MODE == 1 && PF == 3; // two-stage sieve (worklist path only): its own instantiation,
+	                                           // without the word-parallel main pass and the end bitsets
 	// per-start stage behind the sieve words (accept2): always in two-stage mode, and when
 	// the first helix has probes (seq= of single strands at a place the helix fixes)
 	const bool ST2 = TWO || (MODE == 1 && SIEVE && A.par.sv_helix != 0 && A.par.pf_search >= 0 &&
@@ -1206,9 +1207,14 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) gm_search_kernel(const
 #define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, strand, sqbase, (S), (T), (s5), (s3), (hl))
 // 64 bits of the base bitset of base x (table 0) from window-relative position p on
 #define GM_BBITS(x, p) bits64(mypb.base + ((size_t)(strand * mypb.n_dups) * 4 + (x)) * mypb.nwb, sqbase + (p))
+// window-relative positions whose characters the lane can read (score pre-screen)
+#define GM_WIN_LO (-(H - W))
+#define GM_WIN_HI (W + (H - W))
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
+#undef GM_WIN_LO
+#undef GM_WIN_HI
 #undef GM_TAIL
 #undef GM_BBITS
 #undef GM_MASK
@@ -1376,9 +1382,13 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 #define GM_MASK(S, z, clo, n) wc_mask(mypb, L.sq, 0, Lc, (S).dupi, (S).flt, (z), (clo), (n))
 #define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, 0, Lc, (S), (T), (s5), (s3), (hl))
 #define GM_BBITS(x, p) bits64(mypb.base + (size_t)(x) * mypb.nwb, Lc + (p))
+#define GM_WIN_LO (-Lc)
+#define GM_WIN_HI (W + Lc)
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
+#undef GM_WIN_LO
+#undef GM_WIN_HI
 #undef GM_TAIL
 #undef GM_BBITS
 #undef GM_MASK

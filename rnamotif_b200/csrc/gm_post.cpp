@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "gpumotif.h"
@@ -273,3 +275,59 @@ extern "C" int gm_order_hits(const void *hits, size_t n, size_t stride, int n_de
 	return 0;
 }
 
+
+// ---------------------------------------------------------------- score pre-screen (host)
+// The interpreter the device runs at the hit sink (gm_score.h), over one hit record and
+// the searched strand as characters: the CPU check of the device's decision.
+// (GPUMOTIF_SCORE_DEBUG=1: where the host interpreter gave a candidate up, on stderr)
+static void gm_score_trace(int pc, int line)
+{
+	static const bool on = getenv("GPUMOTIF_SCORE_DEBUG") != NULL;
+	if (on)
+		fprintf(stderr, "gm_score: kept at pc %d (gm_score.h:%d)\n", pc, line);
+}
+#define GM_SCORE_TRACE(pc, line) gm_score_trace(pc, line)
+#include "gm_score.h"
+
+namespace {
+struct HostScoreEnv {
+	const gm_plan_t *pl;
+	const gm_hit_hdr_t *hdr;
+	const gm_hit_el_t *els;
+	const char *sbuf;
+	int sl;
+	int ch(int pos) const
+	{
+		if (pos < 0 || pos >= sl)
+			return -1;
+		const int c = (unsigned char)sbuf[pos];
+		// the device knows a character through its IUPAC code: any other letter is unknown to it
+		return strchr("acmgrsvtwyhkdbn", c) != NULL && c != 0 ? c : -1;
+	}
+	int off(int d) const { return els[d].off; }
+	int len(int d) const { return els[d].len; }
+	int mpr(int d) const { return els[d].n_mispairs; }
+	int mm(int d) const { return els[d].n_mismatches; }
+	int comp() const { return hdr->comp; }
+	int pos() const { return hdr->comp ? sl - els[0].off : els[0].off + 1; }
+	int mlen() const
+	{
+		int n = 0;
+		for (int d = 0; d < pl->n_descr; d++)
+			n += els[d].len;
+		return n;
+	}
+	int slen() const { return sl; }
+	const gm_elem_t &elem(int d) const { return pl->elems[d]; }
+	const gm_pairset_t &pairset(int i) const { return pl->pairsets[i]; }
+};
+} // namespace
+
+extern "C" int gm_score_prescreen(const gm_plan_t *plan, const gm_score_t *score, const void *hit, const char *sbuf, int slen)
+{
+	if (plan == NULL || score == NULL || hit == NULL || sbuf == NULL)
+		return 0;
+	const gm_hit_hdr_t *hdr = static_cast<const gm_hit_hdr_t *>(hit);
+	HostScoreEnv env = {plan, hdr, reinterpret_cast<const gm_hit_el_t *>(hdr + 1), sbuf, slen};
+	return gm::score_eval(*score, env) == gm::SC_REJECT ? 1 : 0;
+}

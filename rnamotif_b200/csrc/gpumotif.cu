@@ -71,6 +71,7 @@ struct gm_ctx {
 	// stage what they use into shared memory; nothing is shared between contexts)
 	gm_plan_t *d_plan;
 	DevSearch *d_ds;
+	gm_score_t *d_score;   // score pre-screen (gm_ctx_set_score) or NULL
 	// database
 	uint8_t *d_chars;      // staging for uploaded characters
 	size_t chars_cap;
@@ -173,13 +174,18 @@ static int pf_of(const DevParams &par)
 {
 	return par.sieve ? 2 : par.lit_present ? 1 : 0;
 }
+// ... of the filter kernel of the worklist path: 3 = two-stage sieve
+static int pre_pf(const DevParams &par)
+{
+	return par.sieve && par.sv_two ? 3 : pf_of(par);
+}
 static search_kernel_t dfs_kernel(bool full)
 {
 	return full ? (search_kernel_t)gm_dfs_kernel<true> : (search_kernel_t)gm_dfs_kernel<false>;
 }
 static search_kernel_t pre_kernel(int pf)
 {
-	return pf == 2 ? (search_kernel_t)gm_search_kernel<1, false, 2> : pf == 1 ? (search_kernel_t)gm_search_kernel<1, false, 1> : (search_kernel_t)gm_search_kernel<1, false, 0>;
+	return pf == 3 ? (search_kernel_t)gm_search_kernel<1, false, 3> : pf == 2 ? (search_kernel_t)gm_search_kernel<1, false, 2> : pf == 1 ? (search_kernel_t)gm_search_kernel<1, false, 1> : (search_kernel_t)gm_search_kernel<1, false, 0>;
 }
 
 // Dynamic shared memory every kernel is allowed to ask for.  The attribute belongs to
@@ -1007,9 +1013,9 @@ static int configure_launch(gm_ctx *c, int tile)
 		cudaGetLastError();
 		int na = 0;
 		if (c->b_threads > 0 && c->a_smem <= smem_sm &&
-		    cudaFuncSetAttribute(pre_kernel(pf_of(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN) == cudaSuccess &&
+		    cudaFuncSetAttribute(pre_kernel(pre_pf(c->par)), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN) == cudaSuccess &&
 		    cudaFuncSetAttribute(dfs_kernel(c->full), cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_OPTIN) == cudaSuccess &&
-		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(pf_of(c->par)), c->a_threads, c->a_smem) == cudaSuccess &&
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, pre_kernel(pre_pf(c->par)), c->a_threads, c->a_smem) == cudaSuccess &&
 		    na >= 1) {
 			c->a_blocks = na * c->n_sm;
 			c->use_split = true;
@@ -1034,6 +1040,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->d_chars = c->d_packed = NULL;
 	c->d_plan = NULL;
 	c->d_ds = NULL;
+	c->d_score = NULL;
 	c->d_text = NULL;
 	c->d_hdr_off = NULL;
 	c->d_fsum = c->d_fstart = NULL;
@@ -1150,6 +1157,7 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 		cudaStreamDestroy(c->copy_stream);
 	cudaFree(c->d_plan);
 	cudaFree(c->d_ds);
+	cudaFree(c->d_score);
 	cudaFree(c->d_chars);
 	cudaFree(c->d_text);
 	cudaFree(c->d_hdr_off);
@@ -1174,6 +1182,32 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 }
 
 extern "C" void *gm_stream(const gm_ctx *c) { return c ? (void *)c->stream : NULL; }
+
+extern "C" int gm_ctx_set_score(gm_ctx *c, const gm_score_t *score)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	if (c->pending)
+		return fail("a scan is in flight");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	if (score == NULL || !score->present) {
+		cudaFree(c->d_score);
+		c->d_score = NULL;
+		return 0;
+	}
+	if (score->n_inst <= 0 || score->n_inst > GM_SC_MAX_INST || score->n_var < 0 || score->n_var > GM_SC_MAX_VAR ||
+	    score->n_xel < 0 || score->n_xel > GM_SC_MAX_XEL || score->n_str < 0 || score->n_str > GM_SC_MAX_STR ||
+	    score->n_dbl < 0 || score->n_dbl > GM_SC_MAX_DBL)
+		return fail("score program: table sizes out of range");
+	for (int x = 0; x < score->n_xel; x++)
+		if (score->xel[x].elem >= c->plan.n_descr)
+			return fail("score program does not belong to this plan");
+	if (c->d_score == NULL)
+		CU(cudaMalloc(&c->d_score, sizeof(gm_score_t)));
+	CU(cudaMemcpy(c->d_score, score, sizeof(gm_score_t), cudaMemcpyHostToDevice));
+	return 0;
+}
 
 extern "C" int gm_set_hit_capacity(gm_ctx *c, size_t n)
 {
@@ -1448,6 +1482,8 @@ static int launch(gm_ctx *c)
 	A.par = c->par;
 	A.plan = c->d_plan;
 	A.ds = c->d_ds;
+	A.score = c->d_score;
+	A.score_rejected = c->d_counters + 30;
 	A.packed = c->d_packed;
 	A.total_nt = c->total_nt;
 	A.rec_off = c->d_rec_off;
@@ -1556,7 +1592,7 @@ static int launch(gm_ctx *c)
 				c->seg_ev.push_back(e);
 			}
 			CU(cudaEventRecord(c->seg_ev[2 * c->n_seg_ev], c->stream));
-			pre_kernel(pf_of(c->par))<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
+			pre_kernel(pre_pf(c->par))<<<ablocks, c->a_threads, c->a_smem, c->stream>>>(A);
 			CU(cudaGetLastError());
 			CU(cudaEventRecord(c->seg_ev[2 * c->n_seg_ev + 1], c->stream));
 			c->n_seg_ev++;
@@ -1779,6 +1815,12 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	}
 	c->stats.d2h_bytes = n * sw * 4 + sizeof cnt;
 	c->stats.n_hits = n;
+	c->stats.n_score_rejected = 0;
+	if (c->d_score != NULL) {
+		unsigned long long rej = 0;
+		CU(cudaMemcpy(&rej, c->d_counters + 30, sizeof rej, cudaMemcpyDeviceToHost));
+		c->stats.n_score_rejected = rej;
+	}
 	c->stats.n_starts = cnt[2];
 	if (c->par.sieve) {
 		// the sieve does not visit the starts one by one: count them here

@@ -25,7 +25,8 @@ class ScanStats(C.Structure):
                 ("n_launches", C.c_uint32), ("n_retries", C.c_uint32),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("filter_ms", C.c_double), ("n_survivors", C.c_uint64),
-                ("n_filter_launches", C.c_uint32), ("pad_", C.c_uint32)]
+                ("n_filter_launches", C.c_uint32), ("pad_", C.c_uint32),
+                ("n_score_rejected", C.c_uint64)]
 
 
 class GpuMotifError(RuntimeError):
@@ -38,7 +39,8 @@ EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_host_alloc", "g
            "gm_plan_check", "gm_plan_describe", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
            "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
-           "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits", "gm_order_hits"]
+           "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits", "gm_order_hits",
+           "gm_ctx_set_score", "gm_score_prescreen"]
 
 
 def lib():
@@ -72,6 +74,8 @@ def lib():
         L.gm_set_tile.argtypes = [C.c_void_p, C.c_int]
         L.gm_stream.argtypes = [C.c_void_p]
         L.gm_stream.restype = C.c_void_p
+        L.gm_ctx_set_score.argtypes = [C.c_void_p, C.c_char_p]
+        L.gm_score_prescreen.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int]
         L.gm_prune_hits.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
         L.gm_order_hits.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p]
@@ -175,6 +179,12 @@ class MotifSearch:
     def _ck(self, rc, what):
         if rc != 0:
             raise GpuMotifError(f"{what}: {_err()}")
+
+    def set_score(self, score: bytes | None):
+        """gm_ctx_set_score: the flattened MAIN score program (include/gpumotif_score.h);
+        the sink then drops the candidates it rejects.  None switches it off."""
+        self._score = bytes(score) if score is not None else None
+        self._ck(lib().gm_ctx_set_score(self._ctx, self._score), "gm_ctx_set_score")
 
     def set_tile(self, n: int):
         self._ck(lib().gm_set_tile(self._ctx, n), "gm_set_tile")

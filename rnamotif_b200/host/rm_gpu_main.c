@@ -60,6 +60,7 @@ extern STREL_T *rm_lctx, *rm_rctx;
 
 extern int gm_rm_compile(int, char *[]);
 extern int gm_flatten_plan(gm_plan_t *, char *, size_t);
+extern int gm_flatten_score(gm_score_t *);
 extern void GM_replay_strand(char[], char[], int, int, char[]);
 extern int GM_replay_hit_to(const gm_hit_hdr_t *, const gm_hit_el_t *, FILE *);
 
@@ -92,6 +93,8 @@ static void *xrealloc(void *p, size_t n)
 /* ------------------------------------------------------------------ run-wide state */
 
 static gm_plan_t plan;
+static gm_score_t score;  /* the MAIN score program for the device's pre-screen (gm_ctx_set_score) */
+static uint64_t tot_rejected;
 static int chk_both_strs, show_progress, stats, prune;
 static const char *prog;
 static int devices[MAX_GPUS], n_gpus;
@@ -368,6 +371,11 @@ static void run_host_reader(gm_ctx *ctx, int ecnt)
 		memset(&b, 0, sizeof b);
 		if (gm_hits(ctx, &hp, &b.n_hits, &b.stride))
 			die_gm("gm_hits");
+		{
+			gm_scan_stats_t st;
+			gm_stats(ctx, &st);
+			tot_rejected += st.n_score_rejected;
+		}
 		t2 = now_s();
 		b.hits = hp;
 		b.n_rec = n_recs;
@@ -407,6 +415,7 @@ typedef struct {
 	off_t file_off;
 	BATCH_T b;
 	double ms_read, ms_search;
+	uint64_t n_rejected;     /* candidates the score pre-screen dropped on the device */
 	pthread_t thread;
 } SLOT_T;
 
@@ -576,6 +585,11 @@ static void *worker(void *arg)
 			if (gm_hits(s->ctx, &hp, &s->b.n_hits, &s->b.stride))
 				die_gm("gm_hits");
 			s->b.hits = hp;
+			{
+				gm_scan_stats_t st;
+				gm_stats(s->ctx, &st);
+				s->n_rejected = st.n_score_rejected;
+			}
 			if (s->b.n_hits > 0 && gm_hit_windows(s->ctx, ctx_lead, ctx_trail, &s->b.wins, &s->b.win_stride))
 				die_gm("gm_hit_windows");
 			s->b.text = s->text;
@@ -648,6 +662,7 @@ static int run_pipeline(int *bail_file, off_t *bail_off)
 		t_search += t0 - w0; /* time the replay waited for a batch */
 		t_replay += now_s() - t0;
 		tot_nt += (uint64_t)s->b.rec_off[s->b.n_rec];
+		tot_rejected += s->n_rejected;
 		if (stats)
 			fprintf(stderr, "rnamotif_gpu: batch %ld on gpu %d: %d records, %lld nt: read %.1f ms, search %.1f ms, "
 				"replay %.1f ms (waited %.1f ms), %zu candidates\n", seq, s->device, s->b.n_rec,
@@ -723,6 +738,15 @@ int main(int argc, char *argv[])
 	RM_setprog(P_BEGIN);
 	RM_score(0, 0, NULL, NULL);
 	RM_setprog(P_MAIN);
+	/* the score program as the BEGIN section left it: candidates it rejects outright are
+	 * dropped on the device and never replayed (GPUMOTIF_NO_SCORE=1: replay everything) */
+	gm_flatten_score(&score);
+	if (getenv("GPUMOTIF_NO_SCORE") != NULL)
+		score.present = 0;
+	if (stats)
+		fprintf(stderr, "rnamotif_gpu: score pre-screen on the device: %s%s%s%s\n", score.present ? "on" : "off",
+			score.present || !score.why[0] ? "" : " (", score.present ? "" : score.why,
+			score.present || !score.why[0] ? "" : ")");
 
 	if (!host_only) {
 		int bail_file;
@@ -733,6 +757,8 @@ int main(int argc, char *argv[])
 			slots[i].seq = -1;
 			if (gm_ctx_create(&slots[i].ctx, &plan, slots[i].device))
 				die_gm("gm_ctx_create");
+			if (score.present && gm_ctx_set_score(slots[i].ctx, &score))
+				die_gm("gm_ctx_set_score");
 		}
 		{
 			const double t0 = now_s();
@@ -764,6 +790,8 @@ int main(int argc, char *argv[])
 		gm_ctx *ctx;
 		if (gm_ctx_create(&ctx, &plan, devices[0]))
 			die_gm("gm_ctx_create");
+		if (score.present && gm_ctx_set_score(ctx, &score))
+			die_gm("gm_ctx_set_score");
 		rm_dbfp = DB_fnext(rm_dbfp, &rm_args->a_c_dbfname, rm_args->a_n_dbfname, rm_args->a_dbfname);
 		if (rm_dbfp == NULL)
 			exit(1);
@@ -776,6 +804,7 @@ int main(int argc, char *argv[])
 	if (stats) {
 		const double wall = now_s() - t_start;
 		const double snt = (double)tot_nt * (chk_both_strs ? 2 : 1);
+		fprintf(stderr, "rnamotif_gpu: score pre-screen dropped %llu candidates on the device\n", (unsigned long long)tot_rejected);
 		fprintf(stderr, "rnamotif_gpu: %llu nt, %llu candidates replayed, %d gpu(s), wall %.3f s "
 			"(%.2f G strand-nt/s): set-up %.3f s, pipeline %.3f s (%.2f G strand-nt/s; replay %.3f s, replay waiting "
 			"for batches %.3f s), tear-down %.3f s, host reader %.3f s\n",

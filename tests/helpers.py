@@ -34,6 +34,20 @@ def load_extra_plan(name: str):
         return fh.read()
 
 
+def load_score(name: str):
+    """The MAIN score program as the device's pre-screen takes it (include/gpumotif_score.h;
+    tools/make_bench_plans.sh), or None."""
+    path = os.path.join(GOLDEN, "scores", name + ".score.gz")
+    if not os.path.exists(path):
+        return None
+    with gzip.open(path, "rb") as fh:
+        return fh.read()
+
+
+def score_present(score: bytes) -> bool:
+    return int(np.frombuffer(score, dtype=np.int32, count=1)[0]) != 0
+
+
 def load_cands(name: str):
     z = np.load(os.path.join(GOLDEN, "cands", name + ".npz"))
     return z["head"], z["els"], z["ctx"]

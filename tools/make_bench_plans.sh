@@ -24,3 +24,18 @@ one trna.general $ref/Ecoli.trna.example/trna.general.descr
 out=$root/tests/golden/plans_extra
 mkdir -p "$out"
 for d in eloop hlx.gf.iu hlx.gu.iu mpr phlx.pfrac pk.gf.iu pk.gu.iu; do one descr.$d $ref/descr/$d.descr; done
+# the MAIN score programs as the device's pre-screen takes them (include/gpumotif_score.h)
+out=$root/tests/golden/scores
+mkdir -p "$out"
+score() { # name, descriptor path
+  tmp=$(mktemp); tmp2=$(mktemp)
+  (cd "$(dirname "$2")" && EFNDATA=$ref/efndata GM_PLAN_OUT=$tmp GM_SCORE_OUT=$tmp2 "$dump" -descr "$(basename "$2")" 2>&1 | grep "pre-screen")
+  gzip -n -9 -c "$tmp2" > "$out/$1.score.gz"
+  rm -f "$tmp" "$tmp2"
+}
+for d in score.1 score.2 mp.ends ire efn getbest sprintf bulge; do score $d $ref/test/$d.descr; done
+score descr.trna.general $ref/Ecoli.trna.example/trna.general.descr
+for d in score.0 score.3 score.4 nanlin tmrna; do [ -f $ref/descr/$d.descr ] && score descr.$d $ref/descr/$d.descr; done
+# ... and beside the benchmark plans
+for d in score.1 ire efn mp.ends; do cp "$out/$d.score.gz" "$root/rnamotif_b200/plans/$d.score.gz"; done
+cp "$out/descr.trna.general.score.gz" "$root/rnamotif_b200/plans/trna.general.score.gz"
