@@ -717,14 +717,9 @@ int main(int argc, char *argv[])
 	ip = RM_find_id("show_progress");
 	show_progress = ip == NULL ? 0 : ip->i_val.v_value.v_ival;
 
-	if (rm_args->a_dbfmt != NULL && strcmp(rm_args->a_dbfmt, DT_FASTN)) {
-		if (strcmp(rm_args->a_dbfmt, DT_PIR) && strcmp(rm_args->a_dbfmt, DT_GENBANK)) {
-			rm_error = TRUE;
-			LOG_ERROR("unknown data format %s.", rm_args->a_dbfmt);
-			exit(1);
-		}
+	/* (the reference's main() has checked the format name and opened the first file: rm_dbfp) */
+	if (rm_args->a_dbfmt != NULL && strcmp(rm_args->a_dbfmt, DT_FASTN))
 		host_only = 1;
-	}
 	if (rm_args->a_n_dbfname == 0)
 		host_only = 1; /* standard input */
 	/* the sink's tail reads the context around a match when there is one (set_context,
@@ -767,16 +762,19 @@ int main(int argc, char *argv[])
 			t_loop = now_s() - t0;
 		}
 		if (bail_file >= 0) {
-			/* hand over to the host reader at the batch the pipeline stopped at */
+			/* hand over to the host reader at the batch the pipeline stopped at; a file
+			 * that cannot be opened ends the run there like DB_fnext does (src/dbutil.c:25-38) */
+			if (rm_dbfp != NULL && rm_dbfp != stdin)
+				fclose(rm_dbfp);
 			rm_args->a_c_dbfname = bail_file;
 			rm_dbfp = fopen(rm_args->a_dbfname[bail_file], "r");
-			if (rm_dbfp == NULL) {
+			if (rm_dbfp == NULL)
 				fprintf(stderr, "DB_fnext: can't read seq file '%s'.\n", rm_args->a_dbfname[bail_file]);
-				rm_dbfp = DB_fnext(NULL, &rm_args->a_c_dbfname, rm_args->a_n_dbfname, rm_args->a_dbfname);
-			} else if (bail_off > 0)
-				fseeko(rm_dbfp, bail_off, SEEK_SET);
-			if (rm_dbfp != NULL)
+			else {
+				if (bail_off > 0)
+					fseeko(rm_dbfp, bail_off, SEEK_SET);
 				run_host_reader(slots[0].ctx, ecnt);
+			}
 		}
 		{
 			const double t0 = now_s();
@@ -792,10 +790,7 @@ int main(int argc, char *argv[])
 			die_gm("gm_ctx_create");
 		if (score.present && gm_ctx_set_score(ctx, &score))
 			die_gm("gm_ctx_set_score");
-		rm_dbfp = DB_fnext(rm_dbfp, &rm_args->a_c_dbfname, rm_args->a_n_dbfname, rm_args->a_dbfname);
-		if (rm_dbfp == NULL)
-			exit(1);
-		run_host_reader(ctx, 0);
+		run_host_reader(ctx, 0); /* from the start of the first file (or standard input) */
 		gm_ctx_destroy(ctx);
 	}
 

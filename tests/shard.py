@@ -1,4 +1,6 @@
-"""Sharding of a scan across GPUs / ranks.
+"""TEST HELPER: sharding of a scan across ranks as the range form of
+gm_scan allows it; the product's own multi-GPU path deals whole batches of records to
+the GPUs (rnamotif_b200/host/rm_gpu_main.c) and bench.py gives every rank its own database.
 
 Start positions are independent, so a database shards with no exchange step:
 the concatenated records are cut into `world` contiguous ranges of start

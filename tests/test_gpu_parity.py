@@ -258,3 +258,19 @@ def test_hit_dense_input_and_long_windows():
         ms.close()
         helpers.assert_same_hits(hits, ref, name)
         assert len(ref) > 0, name
+
+
+@pytest.mark.parametrize("name,nt", [("ire", 30_000_000), ("score.1", 5_490_000)])
+def test_one_very_long_record(name, nt):
+    """A single record of chromosome size (the reference's MAXSLEN is 30 000 000,
+    src/rnamot.h): tiles and worklist segments all fall inside one record, starts on
+    the complementary strand count from its far end."""
+    plan = helpers.load_plan(name)
+    ids, seq, off = synth.random_records(101, [nt, 70], planted=False)
+    both = bool(gpumotif.plan_field(plan, 8))
+    ref, _ = oracle_port.scan_db(plan, seq, off, both)
+    ms = gpumotif.MotifSearch(plan)
+    hits = ms.find_motif(seq, off)
+    ms.close()
+    helpers.assert_same_hits(hits, ref, f"{name}: one {nt}-nt record")
+    assert len(ref) > 0

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 from oracle import oracle_port
-from rnamotif_b200 import shard, synth
+from rnamotif_b200 import synth
+import shard
 import helpers
 
 
@@ -45,7 +46,8 @@ import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 from oracle import oracle_port
-from rnamotif_b200 import shard, synth
+from rnamotif_b200 import synth
+import shard
 import helpers
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
