@@ -439,7 +439,7 @@ def dominant_kernel(res, steps, n_descr):
         alg = acc["survivors"] / per_step_fl * (32 + 64) + acc["hits"] * (32 + 8 * n_descr) / per_step_fl
         share = (k_sum - f_sum) / t_res
     elif fl > 0:
-        name = "gm_search_kernel<1,FULL,PF> (level-0 sieve / prefilter)"
+        name = "gm_filter_kernel<PF> (level-0 sieve / prefilter of the worklist path)"
         ms = f_sum / fl
         alg = total * steps / fl * 0.5 + acc["survivors"] / per_step_fl * 32
         share = f_sum / t_res

@@ -77,5 +77,33 @@ def full(path):
         print(f"{100 * inst / tot:5.1f}% {100 * samp / tots:5.1f}% {thr / inst:5.1f}  {f}:{ln}  {text}")
 
 
+def traffic_json(path, descr, mnt):
+    """{"workload", dram bytes, issue-slot utilisation, ...} of the first launch in an ncu-rep, for
+    bench.py's roofline.traffic / issue.ncu (profiles/r2_sieve_kernel.json)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+
+    def get(name):
+        i = hdr.index(name)
+        v = float(vals[i].replace(",", ""))
+        u = units[i].lower()
+        return v * (1e9 if u.startswith("gbyte") else 1e6 if u.startswith("mbyte") else 1e3 if u.startswith("kbyte") else 1)
+
+    out = {"workload": {"descr": descr, "mnt": int(mnt)}, "kernel": vals[hdr.index("Kernel Name")],
+           "dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"),
+           "gpu_time_under_ncu": vals[hdr.index("gpu__time_duration.sum")] + " " + units[hdr.index("gpu__time_duration.sum")],
+           "issue": {"issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                     "alu_pipe_pct": get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                     "warp_instructions": get("smsp__inst_executed.sum"),
+                     "threads_per_instruction": get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                     "warps_active_pct": get("sm__warps_active.avg.pct_of_peak_sustained_active")}}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "json":
+        traffic_json(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

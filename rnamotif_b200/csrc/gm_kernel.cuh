@@ -27,8 +27,6 @@ namespace gm {
 
 struct ScanArgs {
 	DevParams par;              // launch parameters (by value: they belong to this launch)
-	const gm_score_t *score;    // the score program's pre-screen (gm_ctx_set_score) or NULL
-	unsigned long long *score_rejected;
 	const gm_plan_t *plan;      // the context's own device copy of the plan ...
 	const DevSearch *ds;        // ... and of the derived per-search table
 	const uint8_t *packed;      // 4-bit codes, nucleotide g in byte g>>1, nibble g&1
@@ -407,6 +405,61 @@ __device__ __noinline__ bool sink_sites(const Lane &L)
 	return true;
 }
 
+// The score program's pre-screen (gm_ctx_set_score, include/gpumotif_score.h): one
+// THREAD PER CANDIDATE over the hit buffer once the search kernels are done -- the
+// interpreter (gm_score.h) is a chain of dependent loads, so it wants many candidates
+// in flight, not a lane of a diverged search warp.  A candidate the program rejects
+// gets bit 31 of its strand word set; the ordering pass leaves those out.
+struct HitScoreEnv {
+	const uint32_t *h;
+	const gm_plan_t *pl;
+	const uint8_t *packed;
+	int64_t roff;
+	int sl, cmp;
+	__device__ int ch(int pos) const
+	{
+		if (pos < 0 || pos >= sl)
+			return -1;
+		const int64_t gf = roff + (cmp ? sl - 1 - pos : pos);
+		int code = (packed[gf >> 1] >> ((gf & 1) * 4)) & 15;
+		if (cmp) // mk_rcmp, src/rnamot.c:200-208
+			code = code == 1 ? 8 : code == 2 ? 4 : code == 4 ? 2 : code == 8 ? 1 : 15;
+		return code ? (int)"?acmgrsvtwyhkdbn"[code] : -1; // code 0: a letter outside the nucleotide codes
+	}
+	__device__ int off(int d) const { return (int)h[8 + 2 * d]; }
+	__device__ int len(int d) const { return (int)(short)(h[9 + 2 * d] & 0xffff); }
+	__device__ int mpr(int d) const { return (int)(int8_t)((h[9 + 2 * d] >> 16) & 0xff); }
+	__device__ int mm(int d) const { return (int)(int8_t)((h[9 + 2 * d] >> 24) & 0xff); }
+	__device__ int comp() const { return cmp; }
+	__device__ int pos() const { return cmp ? sl - off(0) : off(0) + 1; }
+	__device__ int mlen() const
+	{
+		int n = 0;
+		for (int d = 0; d < pl->n_descr; d++)
+			n += len(d);
+		return n;
+	}
+	__device__ int slen() const { return sl; }
+	__device__ const gm_elem_t &elem(int d) const { return pl->elems[d]; }
+	__device__ const gm_pairset_t &pairset(int i) const { return pl->pairsets[i]; }
+};
+
+__global__ void __launch_bounds__(128) gm_score_kernel(uint32_t *__restrict__ hits, unsigned long long n, int sw,
+	const gm_score_t *__restrict__ score, const gm_plan_t *__restrict__ plan, const uint8_t *__restrict__ packed,
+	const int64_t *__restrict__ rec_off, unsigned long long *__restrict__ n_rejected)
+{
+	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+	     i += (unsigned long long)gridDim.x * blockDim.x) {
+		uint32_t *h = hits + i * sw;
+		const int64_t roff = rec_off[h[0]];
+		HitScoreEnv env = {h, plan, packed, roff, (int)(rec_off[h[0] + 1] - roff), (int)(h[3] & 1)};
+		if (score_eval(*score, env) == SC_REJECT) {
+			h[3] |= 0x80000000u;
+			atomicAdd(n_rejected, 1ull);
+		}
+	}
+}
+
 // The hit sink up to RM_score, src/find_motif.c:362-372, in two parts.  The lane
 // that completed a candidate runs the sink's filters (sink_pass); the hit record is
 // then written by the whole warp at the next converged point of the machine loop
@@ -432,49 +485,7 @@ __device__ __forceinline__ void el_counts(const Lane &L, int d, int &mpr, int &m
 	}
 }
 
-// The candidate a lane holds, as the score program's pre-screen reads it (gm_score.h).
-// Characters come from the lane's window: `lo`..`hi` are the window-relative
-// positions it covers; IUPAC code 0 (a letter outside the nucleotide codes) is
-// reported as unknown.
-struct ScoreEnv {
-	const Lane &L;
-	int lo, hi;
-	__device__ int ch(int pos) const
-	{
-		const int rel = pos - L.szero;
-		if (rel < lo || rel >= hi || pos < 0 || pos >= L.slen)
-			return -1;
-		const int code = icode_of(L.sq[rel]);
-		return code ? (int)"?acmgrsvtwyhkdbn"[code] : -1;
-	}
-	__device__ int off(int d) const { return L.szero + m_off(L, d); }
-	__device__ int len(int d) const { return m_len(L, d); }
-	__device__ int mpr(int d) const { int a, b; el_counts(L, d, a, b); return (int8_t)a; }
-	__device__ int mm(int d) const { int a, b; el_counts(L, d, a, b); return (int8_t)b; }
-	__device__ int comp() const { return L.comp; }
-	__device__ int pos() const { return L.comp ? L.slen - off(0) : off(0) + 1; }
-	__device__ int mlen() const
-	{
-		int n = 0;
-		for (int d = 0; d < L.ND; d++)
-			n += m_len(L, d);
-		return n;
-	}
-	__device__ int slen() const { return L.slen; }
-	__device__ const gm_elem_t &elem(int d) const { return PV.elems[d]; }
-	__device__ const gm_pairset_t &pairset(int i) const { return PV.pairsets[i]; }
-};
-
-__device__ __noinline__ bool sink_score(const Lane &L, const ScanArgs &A, int win_lo, int win_hi)
-{
-	ScoreEnv env = {L, win_lo, win_hi};
-	if (score_eval(*A.score, env) != SC_REJECT)
-		return true;
-	atomicAdd(A.score_rejected, 1ull);
-	return false;
-}
-
-__device__ __noinline__ bool sink_pass(Lane &L, const ScanArgs &A, int win_lo, int win_hi, int ctx[4])
+__device__ __noinline__ bool sink_pass(Lane &L, int ctx[4])
 {
 	ctx[0] = ctx[1] = ctx[2] = ctx[3] = -1;
 	if (PV.par.strict_helices && !sink_strict(L))
@@ -482,9 +493,6 @@ __device__ __noinline__ bool sink_pass(Lane &L, const ScanArgs &A, int win_lo, i
 	if ((PV.lctx.present || PV.rctx.present) && !sink_context(L, ctx))
 		return false;
 	if (PV.n_sites > 0 && !sink_sites(L))
-		return false;
-	// the score program's outright rejections (gm_ctx_set_score)
-	if (A.score != NULL && !sink_score(L, A, win_lo, win_hi))
 		return false;
 	return true;
 }

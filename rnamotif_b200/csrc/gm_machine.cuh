@@ -386,7 +386,7 @@ __device__ __noinline__ bool probes_ok(const Lane &L, const DevSearch &S, int s5
 // word-parallel sieve (sieve_word).  A template parameter so that each plan
 // runs only the code it needs (the kernel is instruction-cache bound).
 template <int MODE, bool FULL, int PF>
-__global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) gm_search_kernel(const ScanArgs A)
+__device__ __forceinline__ void gm_search_body(const ScanArgs &A)
 {
 	constexpr bool SIEVE = PF >= 2; // word-parallel level-0 sieve instead of the per-start prefilter (3: two-stage)
 	// literal prefilter: per start (PF == 1) or as one more term of the sieve
@@ -1207,14 +1207,9 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) gm_search_kernel(const
 #define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, strand, sqbase, (S), (T), (s5), (s3), (hl))
 // 64 bits of the base bitset of base x (table 0) from window-relative position p on
 #define GM_BBITS(x, p) bits64(mypb.base + ((size_t)(strand * mypb.n_dups) * 4 + (x)) * mypb.nwb, sqbase + (p))
-// window-relative positions whose characters the lane can read (score pre-screen)
-#define GM_WIN_LO (-(H - W))
-#define GM_WIN_HI (W + (H - W))
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
-#undef GM_WIN_LO
-#undef GM_WIN_HI
 #undef GM_TAIL
 #undef GM_BBITS
 #undef GM_MASK
@@ -1229,6 +1224,20 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 2 : 1) gm_search_kernel(const
 	my_entries = __reduce_add_sync(0xffffffffu, my_entries);
 	if (lane == 0 && my_entries)
 		atomicAdd(A.start_count + 3, (unsigned long long)my_entries);
+}
+
+// The two entry points of the tile kernel.  The fused kernel (filter + machine) takes
+// what registers it needs; the filter kernel of the worklist path is bounded so that two
+// 256-thread blocks share an SM (its shared memory allows no more).
+template <int MODE, bool FULL, int PF>
+__global__ void gm_search_kernel(const ScanArgs A)
+{
+	gm_search_body<MODE, FULL, PF>(A);
+}
+template <int PF>
+__global__ void __launch_bounds__(256, 2) gm_filter_kernel(const ScanArgs A)
+{
+	gm_search_body<1, false, PF>(A);
 }
 
 // The enumeration kernel of the worklist path: idle lanes take the filter's
@@ -1382,13 +1391,9 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 #define GM_MASK(S, z, clo, n) wc_mask(mypb, L.sq, 0, Lc, (S).dupi, (S).flt, (z), (clo), (n))
 #define GM_TAIL(S, T, s5, s3, hl) tail_feasible(mypb, L.sq, 0, Lc, (S), (T), (s5), (s3), (hl))
 #define GM_BBITS(x, p) bits64(mypb.base + (size_t)(x) * mypb.nwb, Lc + (p))
-#define GM_WIN_LO (-Lc)
-#define GM_WIN_HI (W + Lc)
 #define GM_FULL FULL
 #include "gm_machine_body.inc"
 #undef GM_FULL
-#undef GM_WIN_LO
-#undef GM_WIN_HI
 #undef GM_TAIL
 #undef GM_BBITS
 #undef GM_MASK

@@ -123,6 +123,7 @@ struct gm_ctx {
 	int n_seg_ev;                  // pairs recorded by the last launch
 	const uint32_t *hits_view;     // what gm_hits() hands out
 	size_t n_hits;
+	size_t n_raw;                  // candidates in the device buffer (n_hits + those the score pre-screen rejected)
 	gm_scan_stats_t stats;
 	// pending launch
 	bool pending;
@@ -185,7 +186,8 @@ static search_kernel_t dfs_kernel(bool full)
 }
 static search_kernel_t pre_kernel(int pf)
 {
-	return pf == 3 ? (search_kernel_t)gm_search_kernel<1, false, 3> : pf == 2 ? (search_kernel_t)gm_search_kernel<1, false, 2> : pf == 1 ? (search_kernel_t)gm_search_kernel<1, false, 1> : (search_kernel_t)gm_search_kernel<1, false, 0>;
+	return pf == 3 ? (search_kernel_t)gm_filter_kernel<3> : pf == 2 ? (search_kernel_t)gm_filter_kernel<2> :
+		pf == 1 ? (search_kernel_t)gm_filter_kernel<1> : (search_kernel_t)gm_filter_kernel<0>;
 }
 
 // Dynamic shared memory every kernel is allowed to ask for.  The attribute belongs to
@@ -1482,8 +1484,6 @@ static int launch(gm_ctx *c)
 	A.par = c->par;
 	A.plan = c->d_plan;
 	A.ds = c->d_ds;
-	A.score = c->d_score;
-	A.score_rejected = c->d_counters + 30;
 	A.packed = c->d_packed;
 	A.total_nt = c->total_nt;
 	A.rec_off = c->d_rec_off;
@@ -1657,7 +1657,8 @@ __global__ void gm_sortkey_kernel(const uint32_t *__restrict__ hits, unsigned lo
 	for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
 	     i += (unsigned long long)gridDim.x * blockDim.x) {
 		const uint32_t *h = hits + i * sw;
-		keys[i] = ((unsigned long long)h[0] << 32) | ((unsigned long long)(h[3] & 1) << 31) |
+		// (candidates the score pre-screen rejected -- bit 31 of the strand word -- go last)
+		keys[i] = (h[3] >> 31) ? ~0ull : ((unsigned long long)h[0] << 32) | ((unsigned long long)(h[3] & 1) << 31) |
 			(unsigned long long)(h[1] & 0x7fffffffu);
 		idx[i] = (uint32_t)i;
 	}
@@ -1740,60 +1741,81 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	}
 	wait_range.pop();
 	NvtxRange nvtx_("gpumotif: order + gather candidates");
-	const size_t n = (size_t)cnt[1];
+	const size_t n_all = (size_t)cnt[1];
 	const size_t sw = (size_t)c->stride_words;
-	if (n * sw > c->h_raw_cap) {
+	// the score program's outright rejections, one thread per candidate (gm_ctx_set_score)
+	size_t n_rej = 0;
+	if (c->d_score != NULL && n_all > 0) {
+		NvtxRange nvtx_s("gpumotif: score pre-screen");
+		CU(cudaMemsetAsync(c->d_counters + 30, 0, sizeof(unsigned long long), c->stream));
+		const int sblocks = (int)std::min<size_t>((n_all + 127) / 128, (size_t)c->n_sm * 32);
+		gm_score_kernel<<<sblocks, 128, 0, c->stream>>>(c->d_hits, n_all, (int)sw, c->d_score, c->d_plan, c->d_packed,
+			c->d_rec_off, c->d_counters + 30);
+		CU(cudaGetLastError());
+		unsigned long long rej = 0;
+		CU(cudaMemcpyAsync(&rej, c->d_counters + 30, sizeof rej, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		n_rej = (size_t)rej;
+	}
+	const size_t n = n_all - n_rej; // candidates handed to the caller
+	if (n_all * sw > c->h_raw_cap) {
 		cudaFreeHost(c->h_raw);
 		c->h_raw = NULL;
 		c->h_raw_cap = 0;
-		const size_t want = n * sw + n * sw / 4 + 4096;
+		const size_t want = n_all * sw + n_all * sw / 4 + 4096;
 		CU(cudaMallocHost(&c->h_raw, want * 4));
 		c->h_raw_cap = want;
 	}
 	const uint32_t *raw = c->h_raw;
 	auto t0 = std::chrono::steady_clock::now();
 	auto t1 = t0, t2 = t0;
-	c->dev_sorted = n > 0 && n < 0xffffffffull && n * sw * 4 <= ((size_t)2 << 30) && getenv("GPUMOTIF_HOST_SORT") == NULL;
+	c->dev_sorted = n_all > 0 && n_all < 0xffffffffull && n_all * sw * 4 <= ((size_t)2 << 30) && getenv("GPUMOTIF_HOST_SORT") == NULL;
 	if (c->dev_sorted) {
 		// stable radix sort of (key, buffer index) on the device, gather, one copy
 		size_t temp = 0;
 		cub::DeviceRadixSort::SortPairs(NULL, temp, (unsigned long long *)NULL, (unsigned long long *)NULL,
-			(uint32_t *)NULL, (uint32_t *)NULL, (unsigned long long)n, 0, 64, c->stream);
-		const size_t k_bytes = (n * 8 + 255) & ~(size_t)255, i_bytes = (n * 4 + 255) & ~(size_t)255;
+			(uint32_t *)NULL, (uint32_t *)NULL, (unsigned long long)n_all, 0, 64, c->stream);
+		const size_t k_bytes = (n_all * 8 + 255) & ~(size_t)255, i_bytes = (n_all * 4 + 255) & ~(size_t)255;
 		if (ensure(&c->d_sort, &c->sort_cap, 2 * k_bytes + 2 * i_bytes + temp + 256))
 			return -1;
 		size_t sorted_bytes = c->sorted_cap;
-		if (ensure((void **)&c->d_sorted, &sorted_bytes, n * sw * 4))
+		if (ensure((void **)&c->d_sorted, &sorted_bytes, std::max<size_t>(n, 1) * sw * 4))
 			return -1;
 		c->sorted_cap = sorted_bytes;
 		uint8_t *b = (uint8_t *)c->d_sort;
 		unsigned long long *k_in = (unsigned long long *)b, *k_out = (unsigned long long *)(b + k_bytes);
 		uint32_t *i_in = (uint32_t *)(b + 2 * k_bytes), *i_out = (uint32_t *)(b + 2 * k_bytes + i_bytes);
 		void *d_temp = b + 2 * k_bytes + 2 * i_bytes;
-		const int blocks = (int)std::min<size_t>((n * sw + 255) / 256, (size_t)c->n_sm * 16);
-		gm_sortkey_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hits, n, (int)sw, k_in, i_in);
+		const int blocks = (int)std::min<size_t>((n_all * sw + 255) / 256, (size_t)c->n_sm * 16);
+		gm_sortkey_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hits, n_all, (int)sw, k_in, i_in);
 		CU(cudaGetLastError());
-		CU(cub::DeviceRadixSort::SortPairs(d_temp, temp, k_in, k_out, i_in, i_out, (unsigned long long)n, 0, 64, c->stream));
-		gm_gather_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hits, i_out, n, (int)sw, c->d_sorted);
-		CU(cudaGetLastError());
+		CU(cub::DeviceRadixSort::SortPairs(d_temp, temp, k_in, k_out, i_in, i_out, (unsigned long long)n_all, 0, 64, c->stream));
+		if (n > 0) {
+			gm_gather_kernel<<<blocks, 256, 0, c->stream>>>(c->d_hits, i_out, n, (int)sw, c->d_sorted);
+			CU(cudaGetLastError());
+		}
 		CU(cudaStreamSynchronize(c->stream));
 		t1 = std::chrono::steady_clock::now();
-		CU(cudaMemcpy(c->h_raw, c->d_sorted, n * sw * 4, cudaMemcpyDeviceToHost));
+		if (n > 0)
+			CU(cudaMemcpy(c->h_raw, c->d_sorted, n * sw * 4, cudaMemcpyDeviceToHost));
 		t2 = std::chrono::steady_clock::now();
 		c->hits_view = c->h_raw;
 		// (sort_ms = device ordering, d2h_ms = the copy; swapped below)
 	} else {
-	if (n > 0)
-		CU(cudaMemcpy(c->h_raw, c->d_hits, n * sw * 4, cudaMemcpyDeviceToHost));
+	if (n_all > 0)
+		CU(cudaMemcpy(c->h_raw, c->d_hits, n_all * sw * 4, cudaMemcpyDeviceToHost));
 	t1 = std::chrono::steady_clock::now();
 	// enumeration order: record, strand, start, DFS rank.  Two 64-bit keys per
 	// hit: (rec, comp, szero) and (seq, index into the gathered array)
 	std::vector<uint64_t> &keys = c->keys;
 	keys.resize(2 * n);
-	for (size_t i = 0; i < n; i++) {
+	for (size_t i = 0, k = 0; i < n_all; i++) {
 		const uint32_t *h = &raw[i * sw];
-		keys[2 * i] = ((uint64_t)h[0] << 32) | ((uint64_t)(h[3] & 1) << 31) | (uint64_t)(h[1] & 0x7fffffffu);
-		keys[2 * i + 1] = ((uint64_t)h[2] << 32) | (uint64_t)i;
+		if (h[3] >> 31)
+			continue; // rejected by the score pre-screen
+		keys[2 * k] = ((uint64_t)h[0] << 32) | ((uint64_t)(h[3] & 1) << 31) | (uint64_t)(h[1] & 0x7fffffffu);
+		keys[2 * k + 1] = ((uint64_t)h[2] << 32) | (uint64_t)i;
+		k++;
 	}
 	struct K2 { uint64_t a, b; };
 	K2 *kp = reinterpret_cast<K2 *>(keys.data());
@@ -1806,6 +1828,7 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	c->hits_view = c->hits.data();
 	}
 	c->n_hits = n;
+	c->n_raw = n_all;
 	if (c->dev_sorted) {
 		c->stats.sort_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
 		c->stats.d2h_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
@@ -1815,12 +1838,7 @@ extern "C" int gm_scan_finish(gm_ctx *c)
 	}
 	c->stats.d2h_bytes = n * sw * 4 + sizeof cnt;
 	c->stats.n_hits = n;
-	c->stats.n_score_rejected = 0;
-	if (c->d_score != NULL) {
-		unsigned long long rej = 0;
-		CU(cudaMemcpy(&rej, c->d_counters + 30, sizeof rej, cudaMemcpyDeviceToHost));
-		c->stats.n_score_rejected = rej;
-	}
+	c->stats.n_score_rejected = n_rej;
 	c->stats.n_starts = cnt[2];
 	if (c->par.sieve) {
 		// the sieve does not visit the starts one by one: count them here
@@ -1885,7 +1903,8 @@ extern "C" int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, 
 	NvtxRange nvtx_("gpumotif: hit windows");
 	const int wlen = (lead + c->par.w_winsize + trail + 1 + 7) & ~7;
 	const size_t n = c->n_hits;
-	const size_t bytes = n * (size_t)wlen;
+	const size_t n_dev = c->dev_sorted ? n : c->n_raw; // the unsorted buffer still holds the rejected ones
+	const size_t bytes = n_dev * (size_t)wlen;
 	if (ensure((void **)&c->d_win, &c->win_cap, bytes + 16))
 		return -1;
 	if (bytes > c->h_win_cap) {
@@ -1896,9 +1915,9 @@ extern "C" int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, 
 		CU(cudaMallocHost(&c->h_win, want));
 		c->h_win_cap = want;
 	}
-	if (n > 0) {
-		const int blocks = (int)std::min<size_t>(n, (size_t)c->n_sm * 32);
-		gm_window_kernel<<<blocks, 128, 0, c->stream>>>(c->d_seq_chars, c->d_rec_off, c->dev_sorted ? c->d_sorted : c->d_hits, n, c->stride_words,
+	if (n_dev > 0) {
+		const int blocks = (int)std::min<size_t>(n_dev, (size_t)c->n_sm * 32);
+		gm_window_kernel<<<blocks, 128, 0, c->stream>>>(c->d_seq_chars, c->d_rec_off, c->dev_sorted ? c->d_sorted : c->d_hits, n_dev, c->stride_words,
 			lead, wlen, c->d_win);
 		CU(cudaGetLastError());
 		CU(cudaMemcpyAsync(c->h_win, c->d_win, bytes, cudaMemcpyDeviceToHost, c->stream));
