@@ -37,6 +37,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "gpumotif_plan.h"
 #include "gpumotif_score.h"
 
@@ -219,6 +220,15 @@ int gm_order_hits(const void *hits, size_t n, size_t stride, int n_descr, const 
  */
 int gm_ctx_set_score(gm_ctx *c, const gm_score_t *score);
 int gm_score_prescreen(const gm_plan_t *plan, const gm_score_t *score, const void *hit, const char *sbuf, int slen);
+
+/*
+ * rmfmt's listing: what `rmfmt`, `rmfmt -l` (lopt 1) or `rmfmt -la`
+ * (lopt 2) print for rnamotif's output `text` (src/rmfmt.c:52-376 without -a): "#RM"
+ * lines passed through, hit lines sorted like sort(1) does with rmfmt's keys in the C
+ * locale and set in columns, long fields abbreviated.  Host code only.  The driver
+ * uses it under GPUMOTIF_FMT=1|l|la: `rnamotif ... | rmfmt [-l|-la]` in one program.
+ */
+int gm_rmfmt(const char *text, size_t n_bytes, int lopt, FILE *out);
 
 /* Tunables (before the first scan): hit-buffer capacity in records (default
  * 1<<20; grown automatically when a scan overflows), starts per tile. */

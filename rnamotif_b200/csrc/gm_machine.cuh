@@ -1301,7 +1301,7 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 	// one after the other while the rest of the GPU idles
 	const unsigned long long n_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
 	const int per = (int)max(1ull, min(32ull, (wl_n + n_warps - 1) / n_warps));
-	const int rmin = min(A.par.refill_min, per);
+	const int rmin = min(A.par.dfs_refill, per);
 	const unsigned long long gwarp = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
 	int taken = 0;
 

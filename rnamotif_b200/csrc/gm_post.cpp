@@ -331,3 +331,270 @@ extern "C" int gm_score_prescreen(const gm_plan_t *plan, const gm_score_t *score
 	HostScoreEnv env = {plan, hdr, reinterpret_cast<const gm_hit_el_t *>(hdr + 1), sbuf, slen};
 	return gm::score_eval(*score, env) == gm::SC_REJECT ? 1 : 0;
 }
+
+// ---------------------------------------------------------------- rmfmt [-l | -la]
+// src/rmfmt.c:52-376 (the listing form; not -a, the alignment form) over rnamotif's
+// output text: "#RM" lines pass through, hit lines are sorted (score descending, name,
+// strand, position, length -- the keys rmfmt hands to sort(1), :240-262, compared the
+// way sort does in the C locale, whole lines as the last resort) and printed in
+// columns as wide as their widest entry; entries longer than 20 characters are
+// abbreviated "abc...(n)...xyz" (fcmprs, :474-485); definition lines are dropped.
+#include <string>
+
+namespace {
+struct FmtLine {
+	std::string name;
+	std::vector<std::string> sf; // score fields
+	std::vector<std::string> of; // strand, position, length, elements
+	std::string raw;             // the line as rmfmt writes it to its sort file
+};
+
+std::vector<std::string> fmt_split(const std::string &l)
+{
+	std::vector<std::string> f;
+	size_t i = 0;
+	while (i < l.size()) {
+		while (i < l.size() && (l[i] == ' ' || l[i] == '\t' || l[i] == '\n'))
+			i++;
+		size_t j = i;
+		while (j < l.size() && !(l[j] == ' ' || l[j] == '\t' || l[j] == '\n'))
+			j++;
+		if (j > i)
+			f.push_back(l.substr(i, j - i));
+		i = j;
+	}
+	return f;
+}
+
+bool fmt_is_number(const std::string &s) // is_a_number, :431-463
+{
+	size_t i = 0;
+	int mcnt = 0, ecnt = 0, efmt = 0;
+	if (i < s.size() && s[i] == '-')
+		i++;
+	for (; i < s.size() && isdigit((unsigned char)s[i]); i++)
+		mcnt++;
+	if (i < s.size() && s[i] == '.')
+		i++;
+	for (; i < s.size() && isdigit((unsigned char)s[i]); i++)
+		mcnt++;
+	if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
+		efmt = 1;
+		i++;
+		if (i < s.size() && s[i] == '-')
+			i++;
+		for (; i < s.size() && isdigit((unsigned char)s[i]); i++)
+			ecnt++;
+	}
+	return mcnt != 0 && !(efmt && ecnt == 0) && i == s.size();
+}
+
+// what sort -n reads: optional blanks, '-', digits, '.', digits
+long double fmt_num(const std::string &s)
+{
+	size_t i = 0;
+	while (i < s.size() && (s[i] == ' ' || s[i] == '\t'))
+		i++;
+	bool neg = false;
+	if (i < s.size() && s[i] == '-') {
+		neg = true;
+		i++;
+	}
+	long double v = 0, scale = 1;
+	for (; i < s.size() && isdigit((unsigned char)s[i]); i++)
+		v = v * 10 + (s[i] - '0');
+	if (i < s.size() && s[i] == '.')
+		for (i++; i < s.size() && isdigit((unsigned char)s[i]); i++) {
+			scale /= 10;
+			v += (s[i] - '0') * scale;
+		}
+	return neg ? -v : v;
+}
+} // namespace
+
+extern "C" int gm_rmfmt(const char *text, size_t n_bytes, int lopt, FILE *out)
+{
+	if ((text == NULL && n_bytes > 0) || out == NULL || lopt < 0 || lopt > 2)
+		return gm_post_fail("gm_rmfmt: bad argument");
+	const int DFIELD1 = 4, OFIELD1 = 1, MAXW = 20;
+	std::vector<int> ofmt; // 0 left, 1 right
+	int n_ofields = 0;
+	size_t pos = 0;
+	auto next_line = [&](std::string &l) -> bool {
+		if (pos >= n_bytes)
+			return false;
+		const char *e = static_cast<const char *>(memchr(text + pos, '\n', n_bytes - pos));
+		const size_t end = e ? (size_t)(e - text) + 1 : n_bytes;
+		l.assign(text + pos, end - pos);
+		pos = end;
+		return true;
+	};
+	std::string line;
+	// header: up to the first definition line (:121-143)
+	for (size_t save = pos; next_line(line); save = pos) {
+		if (line[0] == '>') {
+			pos = save;
+			break;
+		}
+		const std::vector<std::string> f = fmt_split(line);
+		if (f.empty() || f[0] != "#RM")
+			continue;
+		if (f.size() < 2)
+			continue;
+		if (f[1] == "descr") {
+			// getfmt, :404-428
+			n_ofields = (int)f.size() - 2 + DFIELD1;
+			ofmt.assign(n_ofields, 0);
+			for (int k = 1; k < DFIELD1; k++)
+				ofmt[k] = 1;
+			for (size_t k = 2; k < f.size(); k++) {
+				const std::string t = f[k].substr(0, 2);
+				ofmt[k - 2 + DFIELD1] = (t == "h3" || t == "t2" || t == "q2" || t == "q4") ? 1 : 0;
+			}
+		}
+		fputs(line.c_str(), out);
+	}
+	std::vector<int> omaxw(std::max(n_ofields, 1), 0);
+	std::vector<FmtLine> rows;
+	int smaxw = 0, m_sfields = 0, n_sfields1 = 0, scored = 1, sorted = 1, n_sfields = 0;
+	size_t raw_bytes = 0;
+	while (next_line(line)) {
+		if (line[0] == '#' || line[0] == '>')
+			continue;
+		std::vector<std::string> f = fmt_split(line);
+		const int n_fields = (int)f.size();
+		const int df1 = n_fields - (n_ofields - DFIELD1), of1 = df1 - (DFIELD1 - OFIELD1);
+		n_sfields = df1 - DFIELD1;
+		if (n_fields == 0 || of1 < 1 || n_sfields < 0)
+			return gm_post_fail("gm_rmfmt: a hit line does not fit the #RM descr line");
+		m_sfields = std::max(m_sfields, n_sfields);
+		if (n_sfields > 1)
+			scored = 0;
+		if (n_sfields1 == 0)
+			n_sfields1 = n_sfields;
+		else if (n_sfields != m_sfields)
+			sorted = 0;
+		FmtLine r;
+		r.name = f[0];
+		for (int k = 0; k < n_sfields; k++)
+			r.sf.push_back(f[k + 1]);
+		for (int k = of1; k < n_fields; k++)
+			r.of.push_back(f[k]);
+		if (scored)
+			scored = !r.sf.empty() && fmt_is_number(r.sf[0]);
+		if (lopt) {
+			// -l: the locus name is what follows the last '|' (or lies between the last two
+			// when nothing follows); -la: the accession between the last two (:181-212)
+			size_t vb = std::string::npos, lvb = std::string::npos;
+			for (size_t k = 0; k < r.name.size(); k++)
+				if (r.name[k] == '|') {
+					lvb = vb;
+					vb = k;
+				}
+			if (vb != std::string::npos) {
+				if (lopt == 1) {
+					if (vb + 1 < r.name.size())
+						r.name = r.name.substr(vb + 1);
+					else if (lvb != std::string::npos)
+						r.name = r.name.substr(lvb + 1, vb - lvb - 1);
+					else
+						r.name = r.name.substr(0, vb);
+				} else if (lvb != std::string::npos)
+					r.name = r.name.substr(lvb + 1, vb - lvb - 1);
+			}
+		}
+		omaxw[0] = std::max(omaxw[0], (int)r.name.size());
+		int fw = 0;
+		for (const std::string &x : r.sf)
+			fw += (int)x.size();
+		fw += n_sfields - 1;
+		smaxw = std::max(smaxw, fw);
+		for (int k = OFIELD1; k < n_ofields && k - 1 < (int)r.of.size(); k++) {
+			std::string &x = r.of[k - 1];
+			if (k >= DFIELD1 && (int)x.size() > MAXW) {
+				char tmp[128];
+				snprintf(tmp, sizeof tmp, "%.3s...(%d)...%.3s", x.c_str(), (int)x.size(), x.c_str() + x.size() - 3);
+				x = tmp;
+			}
+			omaxw[k] = std::max(omaxw[k], (int)x.size());
+		}
+		r.raw = r.name;
+		for (const std::string &x : r.sf)
+			r.raw += " " + x;
+		for (const std::string &x : r.of)
+			r.raw += " " + x;
+		raw_bytes += r.raw.size() + 1;
+		rows.push_back(std::move(r));
+	}
+	if (raw_bytes > 30000000) // SMAX: files larger than this are not sorted (:216-217)
+		scored = sorted = 0;
+	if (scored || sorted) {
+		const int ns = n_sfields; // (of the last line, as rmfmt's command line has it)
+		auto key = [&](const FmtLine &r, int k) -> long double { // field k (1-based) of the raw line, numeric
+			if (k == 1)
+				return fmt_num(r.name);
+			if (k - 2 < (int)r.sf.size())
+				return fmt_num(r.sf[k - 2]);
+			const int o = k - 2 - (int)r.sf.size();
+			return o < (int)r.of.size() ? fmt_num(r.of[o]) : 0;
+		};
+		std::stable_sort(rows.begin(), rows.end(), [&](const FmtLine &a, const FmtLine &b) {
+			if (scored) {
+				const long double x = key(a, 2), y = key(b, 2);
+				if (x != y)
+					return x > y; // -k 2rn,2
+			}
+			const int c = a.name.compare(b.name); // -k 1,1
+			if (c != 0)
+				return c < 0;
+			const int k0 = scored ? 3 : ns + 2;
+			for (int k = k0; k < k0 + 3; k++) {
+				const long double x = key(a, k), y = key(b, k);
+				if (x != y)
+					return x < y;
+			}
+			return a.raw < b.raw; // sort's last resort: the whole line, bytewise in the C locale
+		});
+	}
+	for (const FmtLine &r : rows) {
+		auto put = [&](int k, const std::string &x) {
+			const int w = (int)x.size();
+			if (ofmt[k] == 0) {
+				if (k != 0)
+					fputc(' ', out);
+				fputs(x.c_str(), out);
+				for (int s = 0; s < omaxw[k] - w; s++)
+					fputc(' ', out);
+			} else {
+				fputc(' ', out);
+				for (int s = 0; s < omaxw[k] - w; s++)
+					fputc(' ', out);
+				fputs(x.c_str(), out);
+			}
+		};
+		put(0, r.name);
+		fputc(' ', out);
+		if (m_sfields == 1) {
+			const std::string &x = r.sf.empty() ? std::string() : r.sf[0];
+			for (int s = 0; s < smaxw - (int)x.size(); s++)
+				fputc(' ', out);
+			fputs(x.c_str(), out);
+		} else {
+			int fs = 0;
+			for (size_t k = 0; k < r.sf.size(); k++) {
+				if (k != 0) {
+					fputc(' ', out);
+					fs++;
+				}
+				fputs(r.sf[k].c_str(), out);
+				fs += (int)r.sf[k].size();
+			}
+			for (; fs < smaxw; fs++)
+				fputc(' ', out);
+		}
+		for (int k = OFIELD1; k < n_ofields && k - 1 < (int)r.of.size(); k++)
+			put(k, r.of[k - 1]);
+		fputc('\n', out);
+	}
+	return 0;
+}

@@ -100,6 +100,8 @@ struct DevParams {
 	int n_dups;             // distinct duplex tables with pair bitsets
 	unsigned dups[GM_MAX_DUPS];
 	int refill_min;         // idle lanes a warp waits for before it hands out new starts
+	int dfs_refill;         // the same in the enumeration kernel, where every refill builds lane windows
+	                        // (measured, 512 Mnt: pk_j1+2 12.1 -> 13.9 at 16 instead of 4, trna.general 20.2 -> 22.3 at 24 instead of 8)
 	int pf_search;          // search whose candidate mask is the level-0 prefilter, or -1
 	int pf_z;               // its 5' start relative to the window (fixed-length ss before it)
 	int sieve;              // level-0 sieve (sieve_word): word-parallel test of pf_search's span ends

@@ -785,8 +785,9 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 		const bool strong = par->pf_search >= 0 && ((flt0 >> 8) & 0xff) == 0 && (flt0 & 0xff) >= 3;
 		par->refill_min = !par->lite ? 4 : strong ? GM_REFILL_MIN : 8;
 	}
+	par->dfs_refill = par->lite ? 24 : 16;
 	if (getenv("GPUMOTIF_REFILL") != NULL)
-		par->refill_min = std::max(1, std::min(32, atoi(getenv("GPUMOTIF_REFILL"))));
+		par->refill_min = par->dfs_refill = std::max(1, std::min(32, atoi(getenv("GPUMOTIF_REFILL"))));
 	for (int d = 0; d < ND; d++) {
 		const gm_elem_t &e = pl->elems[d];
 		int src = e.searchno;

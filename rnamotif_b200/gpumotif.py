@@ -40,7 +40,7 @@ EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_host_alloc", "g
            "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
            "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits", "gm_order_hits",
-           "gm_ctx_set_score", "gm_score_prescreen"]
+           "gm_ctx_set_score", "gm_score_prescreen", "gm_rmfmt"]
 
 
 def lib():

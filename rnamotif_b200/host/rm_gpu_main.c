@@ -35,6 +35,9 @@
  * rmprune's decision on their records (src/rmprune.c), and only the kept ones are
  * written.  Blocks are cut at batch boundaries; hits a score program HOLDs and
  * RELEASEs are printed by score.c itself and pass through unpruned.
+ * GPUMOTIF_FMT=1 | l | la: the output of `rnamotif | rmfmt`, `| rmfmt -l`, `| rmfmt -la`
+ * in one program (gm_rmfmt, src/rmfmt.c): stdout is collected in a temporary file
+ * and formatted at the end.
  */
 #define _GNU_SOURCE /* open_memstream, pread */
 #include <ctype.h>
@@ -742,6 +745,8 @@ int main(int argc, char *argv[])
 	const char *ev;
 	int g, i, host_only = 0, ecnt = 0;
 	double t_start = now_s();
+	int fmt = -1, saved_stdout = -1; /* GPUMOTIF_FMT */
+	FILE *fmt_tmp = NULL;
 
 	prog = argv[0];
 	gm_rm_compile(argc, argv);
@@ -765,6 +770,19 @@ int main(int argc, char *argv[])
 		prune = atoi(ev);
 	if ((ev = getenv("GPUMOTIF_READER")) != NULL && !strcmp(ev, "host"))
 		host_only = 1;
+	if ((ev = getenv("GPUMOTIF_FMT")) != NULL && *ev)
+		fmt = !strcmp(ev, "la") ? 2 : !strcmp(ev, "l") ? 1 : 0;
+	if (fmt >= 0) {
+		/* everything written to stdout from here on (print_match, the score program's own
+		 * output) goes to a temporary file first */
+		fflush(stdout);
+		saved_stdout = dup(1);
+		fmt_tmp = tmpfile();
+		if (saved_stdout < 0 || fmt_tmp == NULL || dup2(fileno(fmt_tmp), 1) < 0) {
+			fprintf(stderr, "rnamotif_gpu: GPUMOTIF_FMT: can't redirect stdout\n");
+			exit(1);
+		}
+	}
 
 	ip = RM_find_id("chk_both_strs");
 	chk_both_strs = ip == NULL ? 1 : ip->i_val.v_value.v_ival;
@@ -850,6 +868,22 @@ int main(int argc, char *argv[])
 
 	RM_setprog(P_END);
 	RM_score(0, 0, NULL, NULL);
+	if (fmt >= 0) {
+		char *text;
+		off_t n;
+		fflush(stdout);
+		n = lseek(1, 0, SEEK_END);
+		text = n > 0 ? malloc((size_t)n) : NULL;
+		if (n > 0 && (text == NULL || pread(1, text, (size_t)n, 0) != (ssize_t)n)) {
+			fprintf(stderr, "rnamotif_gpu: GPUMOTIF_FMT: can't read the collected output back\n");
+			exit(1);
+		}
+		dup2(saved_stdout, 1);
+		close(saved_stdout);
+		if (gm_rmfmt(text, n > 0 ? (size_t)n : 0, fmt, stdout))
+			die_gm("gm_rmfmt");
+		free(text);
+	}
 	if (stats) {
 		const double wall = now_s() - t_start;
 		const double snt = (double)tot_nt * (chk_both_strs ? 2 : 1);

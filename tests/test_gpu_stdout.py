@@ -94,3 +94,13 @@ def test_make_test_chk_goldens(name):
     assert fmt.returncode == 0, fmt.stderr.decode(errors="replace")[-500:]
     with open(os.path.join(DATA, "test", name + ".chk"), "rb") as fh:
         assert fmt.stdout == fh.read(), f"{name}: differs from the reference's {name}.chk"
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref (test data) or rnamotif_gpu not built")
+@pytest.mark.parametrize("name", sorted(MD5))
+def test_fmt_option_chk_goldens(name):
+    """GPUMOTIF_FMT=l: rnamotif_gpu prints what `rnamotif ... | rmfmt -l` prints (gm_rmfmt):
+    the reference's 24 .chk files with no reference program in the pipe."""
+    out = run(GPU_BIN, name, {"GPUMOTIF_FMT": "l"})
+    with open(os.path.join(DATA, "test", name + ".chk"), "rb") as fh:
+        assert out == fh.read(), f"{name}: differs from the reference's {name}.chk"

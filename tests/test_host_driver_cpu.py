@@ -69,3 +69,26 @@ def test_prune_option_equals_rnamotif_piped_through_rmprune(name, env):
     got = run(name, dict(env, GPUMOTIF_PRUNE="1"))
     assert got == want
     assert len(want) < len(raw) or name == "nanlin"
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref/rnamotif_hostcheck not built")
+@pytest.mark.parametrize("name", ["trna", "trna.strict", "score.1", "score.2.strict", "efn.strict", "sprintf", "bulge",
+                                  "mp.ends.strict", "nanlin", "pk1", "qu+tr.strict"])
+def test_fmt_option_equals_the_chk_goldens(name):
+    """GPUMOTIF_FMT=l: the driver formats its own output like `rmfmt -l` (gm_rmfmt,
+    src/rmfmt.c:52-376) -- compared with the reference's test/<name>.chk, i.e. with
+    what `rnamotif ... | rmfmt -l` printed for the reference's authors."""
+    out = run(name, {"GPUMOTIF_FMT": "l"})
+    with open(os.path.join(DATA, "test", name + ".chk"), "rb") as fh:
+        assert out == fh.read()
+
+
+RMFMT = os.path.join(helpers.REF, "rmfmt")
+
+
+@pytest.mark.skipif(not (have and os.path.exists(RMFMT)), reason="oracle/_ref (rmfmt, rnamotif_hostcheck) not built")
+@pytest.mark.parametrize("opt,flag", [("1", []), ("la", ["-la"])])
+def test_fmt_option_equals_rmfmt_other_modes(opt, flag):
+    raw = run("efn")
+    want = subprocess.run([RMFMT, *flag], input=raw, capture_output=True, timeout=600, check=True).stdout
+    assert run("efn", {"GPUMOTIF_FMT": opt}) == want and len(want) > 0
