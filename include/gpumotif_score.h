@@ -80,6 +80,8 @@ typedef struct gm_score {
 	int32_t n_inst, n_var, n_xel, n_str, n_dbl;
 	int32_t sym_se;       /* SYM_SE: "any element" in strid (:1390,1403) */
 	int32_t sym_ss;       /* SYM_SS */
+	int32_t has_hold;     /* MAIN contains HOLD or RELEASE (set whatever `present` says) */
+	int32_t pad;
 	char why[96];         /* present = 0: the reason, for the driver's log */
 	gm_sc_inst_t inst[GM_SC_MAX_INST];
 	gm_sc_var_t var[GM_SC_MAX_VAR];

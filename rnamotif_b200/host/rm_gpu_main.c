@@ -808,6 +808,13 @@ int main(int argc, char *argv[])
 	/* the score program as the BEGIN section left it: candidates it rejects outright are
 	 * dropped on the device and never replayed (GPUMOTIF_NO_SCORE=1: replay everything) */
 	gm_flatten_score(&score);
+	if (prune && score.has_hold) {
+		/* held hits are printed by score.c itself, later and past the capture: their order
+		 * would change and they would escape the pruning */
+		fprintf(stderr, "rnamotif_gpu: GPUMOTIF_PRUNE is not available for score programs that HOLD / RELEASE hits; "
+			"pipe the output through rmprune instead\n");
+		exit(1);
+	}
 	if (getenv("GPUMOTIF_NO_SCORE") != NULL)
 		score.present = 0;
 	if (stats)

@@ -112,6 +112,9 @@ int gm_flatten_score(gm_score_t *sc)
 	memset(sc, 0, sizeof *sc);
 	sc->sym_se = SYM_SE;
 	sc->sym_ss = SYM_SS;
+	for (pc = 0; pc < n; pc++)
+		if (pm[pc].i_op == OP_HOLD || pm[pc].i_op == OP_RLSE)
+			sc->has_hold = 1;
 	if (n <= 0)
 		return flat_fail(sc, "no score program");
 	if (l_progs[P_END] > 0)
