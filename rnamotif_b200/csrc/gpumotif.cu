@@ -976,7 +976,29 @@ static int configure_launch(gm_ctx *c, int tile)
 	else if (force != NULL && strcmp(force, "fused") == 0)
 		eligible = false;
 	else
-		eligible = wtot <= 512 && ((c->par.sieve && c->par.pf_deep) || (c->par.lit_present && c->full));
+	{
+		// measured on ire, score.1, mp.ends, efn, descr.quad, descr.trip (1 Gnt, profiles/ab_split2.sh):
+		// the worklist pair beats the fused kernel for every sievable plan (ire 87 -> 172,
+		// score.1 121 -> 159, descr.quad 66 -> 109 G strand-nt/s) -- its filter kernel is small and
+		// keeps no lane state.  Only a first helix that nearly every start passes (estimated
+		// from the share of pairs its table allows) stays fused: the worklist would hold the database.
+		double est = 1.0;
+		if (c->par.sieve && c->par.sv_helix && c->par.pf_search >= 0) {
+			const DevSearch &T = c->ds[c->par.pf_search];
+			int allowed = 0;
+			for (int x = 0; x < 4; x++)
+				for (int y = 0; y < 4; y++)
+					allowed += (T.duplex >> (x * 5 + y)) & 1u;
+			const double q = allowed / 16.0;
+			const int req = T.flt & 0xff, budget = (T.flt >> 8) & 0xff;
+			double pr = pow(q, req);
+			if (budget >= 1)
+				pr += req * (1 - q) * pow(q, req - 1);
+			est = std::min(1.0, (T.dhi - T.dlo + 1) * pr);
+		}
+		const bool strong = c->par.pf_deep || c->par.chain || c->par.lit_present || est <= 0.5;
+		eligible = wtot <= 512 && ((c->par.sieve && strong) || (c->par.lit_present && c->full));
+	}
 	const int fused_tile0 = c->par.tile;
 	if (eligible && tile_arg <= 0 && c->par.sieve) {
 		// the sieve kernel keeps one tile buffer and no lane state: take a large tile
@@ -1285,13 +1307,16 @@ static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src
 		return -1;
 	if (h_chars != NULL && ensure((void **)&c->d_chars, &c->chars_cap, (size_t)n + 64))
 		return -1;
-	// chunk size: at least 64 Mnt, at most 8 chunks (every chunk costs a kernel
+	// chunk size: at least 64 Mnt, at most 16 chunks (every chunk costs a kernel
 	// launch with its own ramp and tail), a multiple of 16 nucleotides
 	// (GPUMOTIF_CHUNK_NT lowers the 64 Mnt floor: tests run the chunk-streamed scan on small inputs)
 	int64_t floor_nt = (int64_t)64 << 20;
 	if (getenv("GPUMOTIF_CHUNK_NT") != NULL && atoll(getenv("GPUMOTIF_CHUNK_NT")) >= 4096)
 		floor_nt = atoll(getenv("GPUMOTIF_CHUNK_NT"));
-	int64_t chunk = std::max<int64_t>(floor_nt, (n + 7) / 8);
+	int n_target = 16; // (trna, 1 Gnt: 72.3 G strand-nt/s end to end with 16 chunks, 69.2 with 8)
+	if (getenv("GPUMOTIF_CHUNKS") != NULL)
+		n_target = std::max(1, std::min(16, atoi(getenv("GPUMOTIF_CHUNKS"))));
+	int64_t chunk = std::max<int64_t>(floor_nt, (n + n_target - 1) / n_target);
 	chunk = (chunk + 15) & ~(int64_t)15;
 	const int n_chunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
 	while ((int)c->chunk_ev.size() < n_chunks) {
