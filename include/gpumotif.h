@@ -104,6 +104,21 @@ void gm_host_free(void *p);
  * must stay valid and unchanged until that scan has returned. */
 int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec);
 
+/* The same batch, packed on the HOST: a thread team (GPUMOTIF_PACK_THREADS, default the
+ * CPUs the process may run on, at most 16) turns the characters into the 4-bit codes
+ * chunk by chunk in pinned staging owned by the context, and half a byte per
+ * nucleotide crosses PCIe instead of one; `seq` may be pageable (the reference's
+ * malloc'ed sbuf, src/rnamot.c:143-149) at no loss.  Returns at once: packing and copies
+ * run on while the caller goes on to gm_scan_launch / gm_scan, which search chunk i
+ * while chunk i+1 is still being packed -- `seq` must stay valid and unchanged until
+ * that call has returned.  The device never holds the characters, so gm_hit_windows
+ * and gm_db_get_chars are refused after this upload (the caller has them).
+ * gm_host_pack is the packer on its own (host code, needs no device): n characters ->
+ * (n + 1) / 2 bytes, nucleotide g in byte g >> 1, nibble g & 1, the code table of
+ * include/gpumotif_plan.h (case folded, u = t, any other character 0). */
+int gm_db_upload_chars_hostpack(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec);
+int gm_host_pack(const char *seq, int64_t n, uint8_t *packed, int n_threads);
+
 /* Same, for characters that already live in device memory (a CUDA device
  * pointer, e.g. torch tensor storage). */
 int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_t *rec_off, int n_rec);

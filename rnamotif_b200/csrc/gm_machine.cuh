@@ -28,6 +28,7 @@
 #pragma once
 
 #include "gm_kernel.cuh"
+#include "gm_tilebits.h"
 
 namespace gm {
 
@@ -543,23 +544,43 @@ __device__ __forceinline__ void gm_search_body(const ScanArgs &A)
 		// base(p) == x) with four ballots per 32 nucleotides
 		uint32_t *pbw = const_cast<uint32_t *>(pb.base);
 		const int nw = Lbytes >> 5;
-		for (int w = 0; w < nw; w++) {
-			const int i = (w << 5) + lane;
-			const int64_t g = lo + i;
-			uint8_t v = (uint8_t)(4 << 4);
-			if (g >= 0 && g < A.total_nt) {
-				unsigned byte = sm_stage[(g >> 1) - bs];
-				v = expand_code((byte >> ((g & 1) * 4)) & 15);
+		{
+			// Eight nucleotides per lane and trip (expand8, gm_tilebits.h: SIMD within a
+			// register, no branches): one funnel shift brings the lane's eight codes in
+			// line whatever the parity of the tile's first nucleotide; the four lanes of
+			// a 32-nucleotide word then exchange the bytes of their base-bitset
+			// contributions (two shuffles + byte permutes), lane 4k + b ending up with
+			// base b's word.
+			const uint32_t *stw = reinterpret_cast<const uint32_t *>(sm_stage);
+			const int n_stw = stage_bytes >> 2;
+			const int base_q = (int)(lo - 2 * bs); // nibble of tile position 0 in the staging buffer (< 0 before the database)
+			const int sh = (base_q & 7) * 4;
+			const bool edge = lo < 0 || lo + Lbytes > A.total_nt; // positions outside the database read as code 0
+			const unsigned sel1 = (lane & 1) ? 0x3715u : 0x6240u, sel2 = (lane & 2) ? 0x3276u : 0x5410u;
+			for (int i0 = lane * 8; i0 < ((Lbytes + 255) & ~255); i0 += 256) {
+				const int wq = (base_q + i0) >> 3;
+				const uint32_t w0 = stw[min(max(wq, 0), n_stw - 1)], w1 = stw[min(max(wq + 1, 0), n_stw - 1)];
+				uint32_t x = __funnelshift_r(w0, w1, sh);
+				if (edge) {
+					const int64_t g0 = lo + i0;
+					const int klo = (int)min((int64_t)8, max((int64_t)0, -g0));
+					const int khi = (int)min((int64_t)8, max((int64_t)0, A.total_nt - g0));
+					const uint32_t m_hi = khi >= 8 ? ~0u : ((1u << (4 * khi)) - 1u);
+					const uint32_t m_lo = klo >= 8 ? 0u : (~0u << (4 * klo));
+					x &= m_hi & m_lo;
+				}
+				uint32_t f0, f1, r0, r1, bits;
+				expand8(x, f0, f1, r0, r1, bits);
+				uint32_t o = __shfl_xor_sync(0xffffffffu, bits, 1);
+				bits = __byte_perm(bits, o, sel1);
+				o = __shfl_xor_sync(0xffffffffu, bits, 2);
+				bits = __byte_perm(bits, o, sel2);
+				if (i0 < Lbytes) {
+					*reinterpret_cast<uint2 *>(sm_fwd + i0) = make_uint2(f0, f1);
+					*reinterpret_cast<uint2 *>(sm_rc + Lbytes - 8 - i0) = make_uint2(r0, r1);
+					pbw[(size_t)(lane & 3) * nwb + (i0 >> 5)] = bits;
+				}
 			}
-			sm_fwd[i] = v;
-			sm_rc[Lbytes - 1 - i] = complement_byte(v);
-			const int bc = bcode_of(v);
-			const unsigned u0 = __ballot_sync(0xffffffffu, bc == 0);
-			const unsigned u1 = __ballot_sync(0xffffffffu, bc == 1);
-			const unsigned u2 = __ballot_sync(0xffffffffu, bc == 2);
-			const unsigned u3 = __ballot_sync(0xffffffffu, bc == 3);
-			if (lane < 4)
-				pbw[(size_t)lane * nwb + w] = lane == 0 ? u0 : lane == 1 ? u1 : lane == 2 ? u2 : u3;
 		}
 		if (lane < 4 * (nwb - nw))
 			pbw[(size_t)(lane / (nwb - nw)) * nwb + nw + lane % (nwb - nw)] = 0; // padding words

@@ -15,7 +15,10 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -24,6 +27,7 @@
 #include "gpumotif.h"
 #include "gm_machine.cuh"
 #include "gm_fastn.cuh"
+#include "gm_hostpack.h"
 
 using namespace gm;
 
@@ -52,6 +56,8 @@ struct NvtxRange {
 	~NvtxRange() { nvtxRangePop(); }
 };
 
+#define GM_PACK_SLOTS 4
+
 struct gm_ctx {
 	gm_plan_t plan;
 	DevParams par;
@@ -67,6 +73,20 @@ struct gm_ctx {
 	std::vector<int64_t> chunk_end;  // nucleotide offsets where the chunks end
 	bool upload_fresh;               // no scan has consumed the last upload yet
 	cudaEvent_t up_ev[2];            // upload start / end on copy_stream
+	// host-packed upload (gm_db_upload_chars_hostpack): a thread team packs chunk i into
+	// a ring of pinned slots while chunk i-1 is on the wire; the uploader thread
+	// enqueues the copies and PUBLISHES each chunk once its event is recorded (waiting
+	// on an event nobody has recorded yet would not wait at all), and gm_scan_launch
+	// takes the chunks as they are published
+	PackTeam *team;
+	std::thread up_thread;
+	std::mutex up_m;
+	std::condition_variable up_cv;
+	int up_published;                // chunks whose event is recorded; -1 = every chunk_ev is (device-side uploads)
+	char up_err[256];                // first error of the uploader thread
+	uint8_t *h_slot[GM_PACK_SLOTS];  // pinned
+	size_t slot_cap;
+	cudaEvent_t slot_ev[GM_PACK_SLOTS]; // the copy out of the slot is done
 	// this context's device copy of the plan and of the per-search table (the kernels
 	// stage what they use into shared memory; nothing is shared between contexts)
 	gm_plan_t *d_plan;
@@ -1130,6 +1150,14 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->copy_stream = NULL;
 	c->upload_fresh = false;
 	c->up_ev[0] = c->up_ev[1] = NULL;
+	c->team = NULL;
+	c->up_published = -1;
+	c->up_err[0] = 0;
+	c->slot_cap = 0;
+	for (int i = 0; i < GM_PACK_SLOTS; i++) {
+		c->h_slot[i] = NULL;
+		c->slot_ev[i] = NULL;
+	}
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
 		delete c;
@@ -1167,10 +1195,18 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 	if (c == NULL)
 		return;
 	cudaSetDevice(c->device);
+	if (c->up_thread.joinable())
+		c->up_thread.join();
+	delete c->team;
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
 	if (c->copy_stream)
 		cudaStreamSynchronize(c->copy_stream);
+	for (int i = 0; i < GM_PACK_SLOTS; i++) {
+		if (c->slot_ev[i])
+			cudaEventDestroy(c->slot_ev[i]);
+		cudaFreeHost(c->h_slot[i]);
+	}
 	for (cudaEvent_t e : c->chunk_ev)
 		cudaEventDestroy(e);
 	for (cudaEvent_t e : c->seg_ev)
@@ -1296,6 +1332,31 @@ static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
 	return 0;
 }
 
+// The uploader thread of the last host-packed upload has enqueued everything (or failed).
+static int join_uploader(gm_ctx *c)
+{
+	if (c->up_thread.joinable())
+		c->up_thread.join();
+	if (c->up_err[0]) {
+		fail("%s", c->up_err);
+		c->up_err[0] = 0;
+		return -1;
+	}
+	return 0;
+}
+
+// chunk_ev[i] has been recorded (host-packed uploads record it from the uploader thread)
+static int wait_published(gm_ctx *c, int i)
+{
+	if (c->up_published < 0)
+		return 0;
+	std::unique_lock<std::mutex> lk(c->up_m);
+	c->up_cv.wait(lk, [&] { return c->up_published > i || c->up_err[0] != 0; });
+	if (c->up_err[0])
+		return fail("%s", c->up_err);
+	return 0;
+}
+
 // Enqueue the upload on copy_stream in chunks: [H2D copy of chunk i,] pack chunk i,
 // record chunk_ev[i].  Returns without waiting.
 static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src, bool mark_start = true)
@@ -1325,6 +1386,7 @@ static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src
 		c->chunk_ev.push_back(e);
 	}
 	c->chunk_end.clear();
+	c->up_published = -1;
 	c->d_seq_chars = h_chars != NULL ? c->d_chars : d_src;
 	if (mark_start)
 		CU(cudaEventRecord(c->up_ev[0], c->copy_stream));
@@ -1353,6 +1415,8 @@ extern "C" int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec
 		return fail("ctx is NULL");
 	if (c->pending)
 		return fail("a scan is in flight");
+	if (join_uploader(c))
+		return -1;
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->copy_stream)); // the previous upload's staging is reused
 	if (set_records(c, rec_off, n_rec))
@@ -1365,12 +1429,116 @@ extern "C" int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec
 	return 0;
 }
 
+// Host-packed upload: the thread team turns chunk i into 4-bit codes in a pinned ring slot,
+// the uploader thread copies it to its place in d_packed and publishes the chunk.  The
+// device never holds the characters (gm_hit_windows / gm_db_get_chars are refused).
+static void uploader_main(gm_ctx *c, const uint8_t *seq, int64_t chunk)
+{
+	auto bail = [&](const char *what, cudaError_t e) {
+		std::lock_guard<std::mutex> lk(c->up_m);
+		snprintf(c->up_err, sizeof c->up_err, "host-packed upload: %s: %s", what, cudaGetErrorString(e));
+		c->up_cv.notify_all();
+	};
+	cudaError_t e = cudaSetDevice(c->device);
+	if (e != cudaSuccess)
+		return bail("cudaSetDevice", e);
+	NvtxRange nvtx_("gpumotif: host pack + H2D of packed chunks");
+	const int n_chunks = (int)c->chunk_end.size();
+	for (int i = 0; i < n_chunks; i++) {
+		const int64_t o = (int64_t)i * chunk, len = c->chunk_end[i] - o;
+		const int sl = i % GM_PACK_SLOTS;
+		if (i >= GM_PACK_SLOTS && (e = cudaEventSynchronize(c->slot_ev[sl])) != cudaSuccess)
+			return bail("cudaEventSynchronize", e);
+		uint8_t *dst = c->h_slot[sl];
+		c->team->run(seq + o, len, dst);
+		// whole 16-byte groups like the device's pack kernel writes them
+		const size_t nb = (size_t)((len + 1) >> 1), nb16 = (nb + 15) & ~(size_t)15;
+		memset(dst + nb, 0, nb16 - nb);
+		if ((e = cudaMemcpyAsync(c->d_packed + (o >> 1), dst, nb16, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess ||
+		    (e = cudaEventRecord(c->slot_ev[sl], c->copy_stream)) != cudaSuccess ||
+		    (e = cudaEventRecord(c->chunk_ev[i], c->copy_stream)) != cudaSuccess)
+			return bail("enqueue", e);
+		if (i == n_chunks - 1 && (e = cudaEventRecord(c->up_ev[1], c->copy_stream)) != cudaSuccess)
+			return bail("cudaEventRecord", e);
+		{
+			std::lock_guard<std::mutex> lk(c->up_m);
+			c->up_published = i + 1;
+		}
+		c->up_cv.notify_all();
+	}
+}
+
+extern "C" int gm_db_upload_chars_hostpack(gm_ctx *c, const char *seq, const int64_t *rec_off, int n_rec)
+{
+	if (c == NULL)
+		return fail("ctx is NULL");
+	if (c->pending)
+		return fail("a scan is in flight");
+	if (join_uploader(c))
+		return -1;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->copy_stream));
+	if (set_records(c, rec_off, n_rec))
+		return -1;
+	const int64_t n = c->total_nt;
+	if (n > 0 && seq == NULL)
+		return fail("seq is NULL");
+	const size_t pbytes = (size_t)(((n + 15) / 16) * 8) + 1024;
+	if (ensure((void **)&c->d_packed, &c->packed_cap, pbytes))
+		return -1;
+	// at most 16 chunks (gm_scan_launch streams up to 16 in) of at least 16 Mnt, a multiple of
+	// 4096 nucleotides; GPUMOTIF_CHUNK_NT lowers the floor (tests)
+	int64_t floor_nt = (int64_t)16 << 20;
+	if (getenv("GPUMOTIF_CHUNK_NT") != NULL && atoll(getenv("GPUMOTIF_CHUNK_NT")) >= 4096)
+		floor_nt = atoll(getenv("GPUMOTIF_CHUNK_NT"));
+	int64_t chunk = std::max<int64_t>(floor_nt, (n + 15) / 16);
+	chunk = (chunk + 4095) & ~(int64_t)4095;
+	const int n_chunks = n > 0 ? (int)((n + chunk - 1) / chunk) : 0;
+	const size_t slot_need = (size_t)(chunk >> 1) + 64;
+	if (c->slot_cap < slot_need) {
+		for (int i = 0; i < GM_PACK_SLOTS; i++) {
+			cudaFreeHost(c->h_slot[i]);
+			c->h_slot[i] = NULL;
+		}
+		c->slot_cap = 0;
+		for (int i = 0; i < GM_PACK_SLOTS; i++)
+			CU(cudaMallocHost((void **)&c->h_slot[i], slot_need));
+		c->slot_cap = slot_need;
+	}
+	for (int i = 0; i < GM_PACK_SLOTS; i++)
+		if (c->slot_ev[i] == NULL)
+			CU(cudaEventCreateWithFlags(&c->slot_ev[i], cudaEventDisableTiming));
+	if (c->team == NULL)
+		c->team = new PackTeam(host_pack_default_threads());
+	while ((int)c->chunk_ev.size() < n_chunks) {
+		cudaEvent_t e;
+		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		c->chunk_ev.push_back(e);
+	}
+	c->chunk_end.clear();
+	for (int i = 0; i < n_chunks; i++)
+		c->chunk_end.push_back(std::min<int64_t>(n, (int64_t)(i + 1) * chunk));
+	c->d_seq_chars = NULL;
+	c->up_published = 0;
+	c->up_err[0] = 0;
+	CU(cudaEventRecord(c->up_ev[0], c->copy_stream));
+	if (n_chunks == 0)
+		CU(cudaEventRecord(c->up_ev[1], c->copy_stream));
+	c->upload_fresh = true;
+	c->stats.h2d_bytes = (uint64_t)((n + 1) >> 1) + (uint64_t)(n_rec + 1) * 8;
+	if (n_chunks > 0)
+		c->up_thread = std::thread(uploader_main, c, (const uint8_t *)seq, chunk);
+	return 0;
+}
+
 extern "C" int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_t *rec_off, int n_rec)
 {
 	if (c == NULL)
 		return fail("ctx is NULL");
 	if (c->pending)
 		return fail("a scan is in flight");
+	if (join_uploader(c))
+		return -1;
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->copy_stream));
 	if (set_records(c, rec_off, n_rec))
@@ -1395,6 +1563,9 @@ extern "C" int gm_db_upload_fastn(gm_ctx *c, const char *text, size_t n_bytes)
 		return fail("text is NULL");
 	if (n_bytes > ((size_t)1 << 40))
 		return fail("text too long");
+	if (join_uploader(c))
+		return -1;
+	c->up_published = -1;
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->copy_stream));
 	NvtxRange nvtx_("gpumotif: upload fastn (H2D + device reader)");
@@ -1539,6 +1710,8 @@ static int launch(gm_ctx *c)
 		int64_t lo = c->p_begin;
 		for (int i = 0; i < n_chunks && lo < c->p_end; i++) {
 			int64_t hi = i == n_chunks - 1 ? c->p_end : std::min<int64_t>(c->p_end, c->chunk_end[i] - c->par.halo - c->par.tile);
+			if (wait_published(c, i))
+				return -1;
 			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[i], 0));
 			if (hi <= lo)
 				continue;
@@ -1558,8 +1731,11 @@ static int launch(gm_ctx *c)
 			lo = hi;
 		}
 	} else if (A.n_tiles > 0 && !c->use_split) {
-		if (n_chunks > 0)
+		if (n_chunks > 0) {
+			if (wait_published(c, n_chunks - 1))
+				return -1;
 			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
+		}
 		int blocks = (int)std::min<int64_t>(c->blocks, A.n_tiles);
 		fused_kernel(c->full, pf_of(c->par))<<<blocks, c->threads, c->smem_bytes, c->stream>>>(A);
 		CU(cudaGetLastError());
@@ -1570,8 +1746,11 @@ static int launch(gm_ctx *c)
 		// chunk's data end (less the halo a tile reads ahead) and waits for that
 		// chunk only, so the search of chunk i overlaps the copy of chunk i+1.
 		const bool stream_in = c->upload_fresh && n_chunks > 1 && n_chunks <= 16;
-		if (n_chunks > 0 && !stream_in)
+		if (n_chunks > 0 && !stream_in) {
+			if (wait_published(c, n_chunks - 1))
+				return -1;
 			CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[n_chunks - 1], 0));
+		}
 		// The worklist holds GM_WL_SEG_NT x 2 entries: enough for every start of a
 		// default segment.  Segments grow beyond that when the previous scans showed
 		// that few starts survive the filter (fewer launches, and the DFS kernel's
@@ -1588,29 +1767,32 @@ static int launch(gm_ctx *c)
 		}
 		A.wl = c->d_wl;
 		A.wl_cap = c->wl_cap;
-		// When the whole range fits one segment (few survivors) but arrives in
-		// chunks, the filter kernel runs per chunk and appends to ONE worklist; the
-		// enumeration kernel runs once at the end (its latency tail is paid once).
-		const bool defer_dfs = stream_in && seg >= c->p_end - c->p_begin;
-		if (defer_dfs)
-			CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
+		// A segment that arrives in chunks has the filter kernel run per chunk, appending
+		// to ONE worklist; the enumeration kernel runs once per segment (its latency
+		// tail -- a few long enumerations -- is paid once, not per chunk).
 		int ci = 0;
+		int64_t seg_end = c->p_begin; // where the worklist segment being filled ends
 		for (int64_t g0 = c->p_begin; g0 < c->p_end; g0 = A.g_end) {
+			if (g0 == seg_end) {
+				// a new segment: worklist count and head restart
+				seg_end = std::min<int64_t>(g0 + seg, c->p_end);
+				CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
+			}
 			A.g_begin = g0;
-			A.g_end = std::min<int64_t>(g0 + seg, c->p_end);
+			A.g_end = seg_end;
 			if (stream_in) {
 				const int64_t slack = (int64_t)c->par.halo + c->par.tile;
 				while (ci < n_chunks - 1 && c->chunk_end[ci] - slack <= g0)
 					ci++;
+				if (wait_published(c, ci))
+					return -1;
 				CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[ci], 0));
 				if (ci < n_chunks - 1)
 					A.g_end = std::min<int64_t>(A.g_end, c->chunk_end[ci] - slack);
 			}
 			A.n_tiles = (A.g_end - A.g_begin + c->par.tile - 1) / c->par.tile;
-			// tile counter, worklist count and head restart for every segment
+			// the tile counter restarts for every filter launch
 			CU(cudaMemsetAsync(c->d_counters + 0, 0, sizeof(unsigned long long), c->stream));
-			if (!defer_dfs)
-				CU(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
 			int ablocks = (int)std::min<int64_t>(c->a_blocks, A.n_tiles);
 			while ((int)c->seg_ev.size() < 2 * (c->n_seg_ev + 1)) {
 				cudaEvent_t e;
@@ -1623,16 +1805,11 @@ static int launch(gm_ctx *c)
 			CU(cudaEventRecord(c->seg_ev[2 * c->n_seg_ev + 1], c->stream));
 			c->n_seg_ev++;
 			c->stats.n_launches++;
-			if (!defer_dfs) {
+			if (A.g_end == seg_end) {
 				dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
 				CU(cudaGetLastError());
 				c->stats.n_launches++;
 			}
-		}
-		if (defer_dfs) {
-			dfs_kernel(c->full)<<<c->b_blocks, c->b_threads, c->b_smem, c->stream>>>(A);
-			CU(cudaGetLastError());
-			c->stats.n_launches++;
 		}
 	}
 	CU(cudaEventRecord(c->ev[4], c->stream));

@@ -36,7 +36,7 @@ class GpuMotifError(RuntimeError):
 _lib = None
 
 EXPORTS = ["gm_last_error", "gm_version", "gm_device_count", "gm_host_alloc", "gm_host_free", "gm_ctx_create", "gm_ctx_destroy",
-           "gm_plan_check", "gm_plan_describe", "gm_db_upload_chars", "gm_db_set_device_chars", "gm_db_upload_fastn",
+           "gm_plan_check", "gm_plan_describe", "gm_db_upload_chars", "gm_db_upload_chars_hostpack", "gm_host_pack", "gm_db_set_device_chars", "gm_db_upload_fastn",
            "gm_db_records", "gm_db_get_chars", "gm_db_total_nt", "gm_hit_windows",
            "gm_scan", "gm_scan_launch", "gm_scan_finish", "gm_hits", "gm_stats",
            "gm_set_hit_capacity", "gm_set_tile", "gm_stream", "gm_prune_hits", "gm_order_hits",
@@ -58,6 +58,8 @@ def lib():
         L.gm_plan_check.argtypes = [C.c_char_p]
         L.gm_plan_describe.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
         L.gm_db_upload_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.gm_db_upload_chars_hostpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.gm_host_pack.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
         L.gm_db_set_device_chars.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gm_db_upload_fastn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.gm_db_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
@@ -200,10 +202,22 @@ class MotifSearch:
         self._ck(lib().gm_db_upload_chars(self._ctx, seq.ctypes.data, rec_off.ctypes.data, len(rec_off) - 1),
                  "gm_db_upload_chars")
 
-    def upload_ptr(self, host_ptr: int, rec_off):
+    def upload_ptr(self, host_ptr: int, rec_off, host_pack=False):
+        """gm_db_upload_chars from a raw host pointer; host_pack=True: gm_db_upload_chars_hostpack
+        (4-bit codes made by a host thread team, half the bytes over PCIe)."""
         rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+        if host_pack:
+            self._ck(lib().gm_db_upload_chars_hostpack(self._ctx, host_ptr, rec_off.ctypes.data, len(rec_off) - 1),
+                     "gm_db_upload_chars_hostpack")
+            return
         self._ck(lib().gm_db_upload_chars(self._ctx, host_ptr, rec_off.ctypes.data, len(rec_off) - 1),
                  "gm_db_upload_chars")
+
+    def upload_hostpack(self, seq, rec_off):
+        """gm_db_upload_chars_hostpack over a uint8 array (pinned or pageable)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        self._keep = seq  # packing runs on until the next scan has been launched
+        self.upload_ptr(seq.ctypes.data, rec_off, host_pack=True)
 
     def set_device_chars(self, dev_ptr: int, rec_off):
         rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
@@ -300,3 +314,12 @@ class MotifSearch:
     def find_motif(self, seq, rec_off):
         self.upload(seq, rec_off)
         return self.scan()
+
+
+def host_pack(seq, n_threads=0):
+    """gm_host_pack: uint8 characters -> 4-bit codes, two per byte (host code, no device)."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    out = np.zeros((seq.size + 1) // 2, dtype=np.uint8)
+    if lib().gm_host_pack(seq.ctypes.data, seq.size, out.ctypes.data, n_threads) != 0:
+        raise GpuMotifError("gm_host_pack failed")
+    return out
