@@ -225,16 +225,18 @@ class Bench:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; libgpumotif has no CPU path")
+        try:
+            self.ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            self.ncpu = os.cpu_count() or 1
+        self.numa_node = numa_bind(self.local)
         torch.cuda.set_device(self.local)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         self.cap = 0
         self.d_chars = self.h_chars = None
         # host threads of the packed upload: this rank's share of the CPUs (gpumotif reads the variable)
-        try:
-            ncpu = len(os.sched_getaffinity(0))
-        except AttributeError:
-            ncpu = os.cpu_count() or 1
+        ncpu = self.ncpu
         self.pack_threads = int(os.environ.get("GPUMOTIF_PACK_THREADS", max(1, min(16, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", self.world)))))))
         os.environ["GPUMOTIF_PACK_THREADS"] = str(self.pack_threads)
         self.lut = torch.tensor(list(b"acgt"), dtype=torch.uint8, device="cuda")
@@ -491,6 +493,43 @@ def write_fasta(path, n_rec, rec_nt, seed, width=70):
     return n_rec * rec_nt
 
 
+def _pipeline_rate(summary):
+    """G strand-nt/s of the driver's read / search / replay pipeline alone (its own timer, between CUDA
+    start-up + context creation and tear-down), from the GPUMOTIF_STATS summary line."""
+    import re
+    m = re.search(r"pipeline [0-9.]+ s \(([0-9.]+) G strand-nt/s", summary or "")
+    return float(m.group(1)) if m else None
+
+
+def numa_bind(local_rank):
+    """Run this rank on the CPUs of its GPU's NUMA node before any pinned buffer is allocated (pinned
+    pages land on the node of the allocating thread; eight ranks reading one node's memory was round 1's
+    end-to-end limiter at 8 GPUs).  Quietly does nothing where the platform does not tell (numa_node -1)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].strip().isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # nvml prints an eight-digit domain, sysfs four
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def binary_leg(descr, mnt, prefix_mnt):
     """The drop-in program itself: rnamotif_b200/host/_build/rnamotif_gpu (the
     reference's front end, score program and printer around libgpumotif) over a FASTA
@@ -526,6 +565,7 @@ def binary_leg(descr, mnt, prefix_mnt):
         out.update(value=nt * strands / dt / 1e9, unit=UNIT, wall_s=dt, file_mnt=mnt,
                    file_bytes=os.path.getsize(big), stdout_bytes=os.path.getsize(os.path.join(tmp, "big.out")),
                    driver_summary=summary[-1] if summary else None,
+                   pipeline_value=_pipeline_rate(summary[-1]) if summary else None,
                    what="wall clock of `rnamotif_gpu -descr %s.descr FILE` from exec to exit (CUDA start-up, file read, "
                         "search, score + print of every candidate, stdout to a file on tmpfs)" % descr)
         dtg, rg = run(exe, pre, os.path.join(tmp, "pre_gpu.out"))
@@ -587,6 +627,7 @@ def run_gpu_arm(args):
                          "note": "the search is integer-issue bound, not HBM bound (SURVEY.md F8); see issue and profiles/"},
             "parity": res["parity"],
             "clocks": res["clocks"],
+            "host": {"cpus": B.ncpu, "numa_node_bound": B.numa_node, "pack_threads": B.pack_threads},
         }
         if W is not None:
             line["issue"] = {"pair_evals_per_strand_nt": W,
