@@ -643,10 +643,12 @@ __device__ __noinline__ void wx_finish_mm(Lane &L, const DevSearch &S, int s5, i
 // find_minlen / find_maxlen, src/find_motif.c:642-665, over elements fd..ld of the
 // pseudoknot of search S, as (min, max) packed: prefix sums over the static lengths,
 // corrected for the elements that can be matched at this point (DevSearch::pkm_off).
-__device__ __noinline__ uint32_t pk_range(const Lane &L, const StagedPlan &sp, const DevSearch &S, int fd, int ld)
+__device__ __noinline__ uint32_t pk_range(const Lane &L, const StagedPlan &sp_, const DevSearch &S_, int fd, int ld)
 {
 	if (fd > ld)
 		return 0;
+	const DevSearch &S = *gm_sh(&S_);
+	struct { const int *pmin, *pmax; const uint32_t *elmm; } sp = {gm_sh(sp_.pmin), gm_sh(sp_.pmax), gm_sh(sp_.elmm)};
 	int mn = sp.pmin[ld + 1] - sp.pmin[fd], mx = sp.pmax[ld + 1] - sp.pmax[fd];
 	for (int i = 0; i < S.pkm_n; i++) {
 		const int d = PV.par.pk_m[S.pkm_off + i];

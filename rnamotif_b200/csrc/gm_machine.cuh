@@ -113,8 +113,9 @@ __device__ __forceinline__ uint8_t complement_byte(uint8_t v)
 }
 
 // 64 bits of a bitset starting at bit q (q >= 0; the set is padded by 4 words)
-__device__ __forceinline__ uint64_t bits64(const uint32_t *set, int q)
+__device__ __forceinline__ uint64_t bits64(const uint32_t *set_, int q)
 {
+	const uint32_t *set = gm_sh(set_); // every bitset lives in shared memory
 	const int w = q >> 5, sh = q & 31;
 	const uint32_t a = set[w], b = set[w + 1], c = set[w + 2];
 	const uint32_t lo = __funnelshift_r(a, b, sh);
@@ -202,8 +203,8 @@ __device__ __forceinline__ uint32_t sieve_word_r(const PairBits &pb, int strand,
 	const int req = REQ > 0 ? REQ : (flt & 0xff);
 	const int budget = (flt >> 8) & 0xff, first_must = (flt >> 16) & 1;
 	const int nwb = pb.nwb;
-	const uint32_t *P = pb.base + ((size_t)(strand * pb.n_dups + dupi) * 4) * nwb;
-	const uint32_t *I = pb.base + ((size_t)(strand * pb.n_dups) * 4) * nwb; // table 0: base bitsets
+	const uint32_t *P = gm_sh(pb.base) + ((size_t)(strand * pb.n_dups + dupi) * 4) * nwb;
+	const uint32_t *I = gm_sh(pb.base) + ((size_t)(strand * pb.n_dups) * 4) * nwb; // table 0: base bitsets
 	uint32_t Bl[4], Bh[4];
 #pragma unroll
 	for (int x = 0; x < 4; x++) {
@@ -279,8 +280,9 @@ __device__ __forceinline__ uint32_t sieve_word_main(const PairBits &pb, int stra
 }
 
 // 32 bits of a bitset from bit q on (q >= 0)
-__device__ __forceinline__ uint32_t bits32(const uint32_t *set, int q)
+__device__ __forceinline__ uint32_t bits32(const uint32_t *set_, int q)
 {
+	const uint32_t *set = gm_sh(set_);
 	return __funnelshift_r(set[q >> 5], set[(q >> 5) + 1], q & 31);
 }
 

@@ -23,6 +23,21 @@
 #include <stdint.h>
 #include "gpumotif_plan.h"
 
+// The bitsets and the lane state live in shared memory, but where their pointers have gone
+// through a struct or a call the compiler no longer knows that and emits generic loads with
+// 64-bit address arithmetic (430 LD.E in the two-stage filter kernel, none after).  Telling it
+// turns them into LDS with 32-bit addresses: fewer instructions (-19 % in the enumeration
+// kernel's SASS), fewer registers (the filter kernel no longer spills).  Used ONLY on the
+// bitset readers (bits64 / bits32 / sieve_word_r) and the lane-state accessors: wrapping the
+// staged plan tables or the sequence bytes as well -- also shared memory -- gave wrong
+// candidates with nvcc 12.9 (bisected on the GPU: profiles/bisect_sh.sh), so those stay generic.
+template <typename T>
+__device__ __forceinline__ T *gm_sh(T *p)
+{
+	__builtin_assume(__isShared((const void *)p));
+	return p;
+}
+
 namespace gm {
 
 // kinds of search heads (what find_1_motif dispatches on, src/find_motif.c:289-330)
@@ -195,10 +210,10 @@ struct Lane {
 };
 
 // ---- lane state accessors -------------------------------------------------
-#define L_ZD(L, s)     (L).st[(s) * (L).nt]
-#define L_FR(L, s, k)  (L).st[((L).NS + (L).ds[s].fr + (k)) * (L).nt]
-#define L_EL(L, d)     (L).st[((L).el_base + (d)) * (L).nt]
-#define L_EM(L, d)     (L).st[((L).el_base + (L).ND + (d)) * (L).nt]
+#define L_ZD(L, s)     gm_sh((L).st)[(s) * (L).nt]
+#define L_FR(L, s, k)  gm_sh((L).st)[((L).NS + gm_sh((L).ds)[s].fr + (k)) * (L).nt]
+#define L_EL(L, d)     gm_sh((L).st)[((L).el_base + (d)) * (L).nt]
+#define L_EM(L, d)     gm_sh((L).st)[((L).el_base + (L).ND + (d)) * (L).nt]
 
 __device__ __forceinline__ void mark(Lane &L, int d, int off, int len)
 {
@@ -230,8 +245,10 @@ __device__ __forceinline__ void set_mpr(Lane &L, int d, int mpr)
 // Boolean result only: for the operator subset the plan admits (classes, '.',
 // '*', \{m,n\}, '^', '$') "some backtracking path succeeds" is regular-language
 // membership, which the position automaton decides exactly.
-__device__ __noinline__ int rx_match(const DevRegex &rx, const uint8_t *s, int n)
+__device__ __noinline__ int rx_match(const DevRegex &rx_, const uint8_t *s_, int n)
 {
+	const DevRegex &rx = rx_;
+	const uint8_t *s = s_;
 	const uint64_t skip = rx.skip, star = rx.star;
 	const uint64_t accept = (uint64_t)1 << rx.npos;
 	const int iters = rx.closure_iters;
@@ -264,8 +281,10 @@ __device__ __noinline__ int rx_match(const DevRegex &rx, const uint8_t *s, int n
 // Returns 1 and the mismatch count of the first (leftmost) placement that
 // stays within l_mm; on failure *n_mm is what the last placement tried left
 // behind (mm_advance counts into the caller's s_n_mismatches as it goes).
-__device__ __noinline__ int rx_match_mm(const DevRegex &rx, const uint8_t *s, int n, int l_mm, int *n_mm)
+__device__ __noinline__ int rx_match_mm(const DevRegex &rx_, const uint8_t *s_, int n, int l_mm, int *n_mm)
 {
+	const DevRegex &rx = rx_;
+	const uint8_t *s = s_;
 	const int m = rx.mm_len;
 	const int last = rx.bol ? 0 : n;
 	int cnt = 0;

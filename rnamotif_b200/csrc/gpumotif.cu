@@ -65,7 +65,12 @@ struct gm_ctx {
 	int device;
 	int n_sm;
 	cudaStream_t stream;       // search kernels, hit gather
-	cudaStream_t copy_stream;  // uploads: H2D copies + pack kernels, in chunks
+	cudaStream_t copy_stream;  // uploads: H2D copies (+ pack kernels of device-side uploads), in chunks
+	// pack kernels of a character upload from the host: on a stream of their own (highest priority), gated per
+	// chunk on the copy, so that the copy engine never waits for a pack kernel that is itself waiting for the
+	// search kernel of the previous chunk to leave an SM
+	cudaStream_t pack_stream;
+	std::vector<cudaEvent_t> cp_ev;  // chunk i has arrived on the device
 	cudaEvent_t ev[6];
 	// an upload is cut into chunks; chunk_ev[i] fires when chunk i is packed, so the
 	// first scan after an upload starts on chunk 0 while the rest is still copying
@@ -1148,6 +1153,7 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	c->stride_words = (int)((sizeof(gm_hit_hdr_t) + plan->n_descr * sizeof(gm_hit_el_t)) / 4);
 	c->hit_cap = (size_t)1 << 20;
 	c->copy_stream = NULL;
+	c->pack_stream = NULL;
 	c->upload_fresh = false;
 	c->up_ev[0] = c->up_ev[1] = NULL;
 	c->team = NULL;
@@ -1162,6 +1168,14 @@ extern "C" int gm_ctx_create(gm_ctx **out, const gm_plan_t *plan, int device)
 	    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
 		delete c;
 		return fail("cudaStreamCreate failed");
+	}
+	{
+		int lo_pri = 0, hi_pri = 0;
+		cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+		if (cudaStreamCreateWithPriority(&c->pack_stream, cudaStreamNonBlocking, hi_pri) != cudaSuccess) {
+			gm_ctx_destroy(c);
+			return fail("cudaStreamCreateWithPriority failed");
+		}
 	}
 	cudaEventCreate(&c->up_ev[0]);
 	cudaEventCreate(&c->up_ev[1]);
@@ -1202,6 +1216,10 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 		cudaStreamSynchronize(c->stream);
 	if (c->copy_stream)
 		cudaStreamSynchronize(c->copy_stream);
+	if (c->pack_stream)
+		cudaStreamSynchronize(c->pack_stream);
+	for (cudaEvent_t e : c->cp_ev)
+		cudaEventDestroy(e);
 	for (int i = 0; i < GM_PACK_SLOTS; i++) {
 		if (c->slot_ev[i])
 			cudaEventDestroy(c->slot_ev[i]);
@@ -1216,6 +1234,8 @@ extern "C" void gm_ctx_destroy(gm_ctx *c)
 			cudaEventDestroy(c->up_ev[i]);
 	if (c->copy_stream)
 		cudaStreamDestroy(c->copy_stream);
+	if (c->pack_stream)
+		cudaStreamDestroy(c->pack_stream);
 	cudaFree(c->d_plan);
 	cudaFree(c->d_ds);
 	cudaFree(c->d_score);
@@ -1332,6 +1352,14 @@ static int set_records(gm_ctx *c, const int64_t *rec_off, int n_rec)
 	return 0;
 }
 
+// the previous upload has left the copy engine and the pack kernels
+static int sync_uploads(gm_ctx *c)
+{
+	CU(cudaStreamSynchronize(c->copy_stream));
+	CU(cudaStreamSynchronize(c->pack_stream));
+	return 0;
+}
+
 // The uploader thread of the last host-packed upload has enqueued everything (or failed).
 static int join_uploader(gm_ctx *c)
 {
@@ -1390,18 +1418,28 @@ static int upload_chunks(gm_ctx *c, const uint8_t *h_chars, const uint8_t *d_src
 	c->d_seq_chars = h_chars != NULL ? c->d_chars : d_src;
 	if (mark_start)
 		CU(cudaEventRecord(c->up_ev[0], c->copy_stream));
+	while (h_chars != NULL && (int)c->cp_ev.size() < n_chunks) {
+		cudaEvent_t e;
+		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		c->cp_ev.push_back(e);
+	}
+	// from the host: copies back to back on the copy stream, pack kernels on the pack stream behind
+	// each chunk's copy; on the device: pack kernels on the copy stream
+	cudaStream_t ps = h_chars != NULL ? c->pack_stream : c->copy_stream;
 	for (int i = 0; i < n_chunks; i++) {
 		const int64_t o = (int64_t)i * chunk, len = std::min<int64_t>(chunk, n - o);
 		const uint8_t *src = d_src;
 		if (h_chars != NULL) {
 			CU(cudaMemcpyAsync(c->d_chars + o, h_chars + o, (size_t)len, cudaMemcpyHostToDevice, c->copy_stream));
+			CU(cudaEventRecord(c->cp_ev[i], c->copy_stream));
+			CU(cudaStreamWaitEvent(ps, c->cp_ev[i], 0));
 			src = c->d_chars;
 		}
 		const int64_t groups = (len + 15) / 16;
 		const int blocks = (int)std::min<int64_t>((groups + 255) / 256, (int64_t)c->n_sm * 16);
-		gm_pack_kernel<<<blocks, 256, 0, c->copy_stream>>>(src + o, c->d_packed + (o >> 1), len);
+		gm_pack_kernel<<<blocks, 256, 0, ps>>>(src + o, c->d_packed + (o >> 1), len);
 		CU(cudaGetLastError());
-		CU(cudaEventRecord(c->chunk_ev[i], c->copy_stream));
+		CU(cudaEventRecord(c->chunk_ev[i], ps));
 		c->chunk_end.push_back(o + len);
 	}
 	CU(cudaEventRecord(c->up_ev[1], c->copy_stream));
@@ -1418,7 +1456,8 @@ extern "C" int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec
 	if (join_uploader(c))
 		return -1;
 	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->copy_stream)); // the previous upload's staging is reused
+	if (sync_uploads(c)) // the previous upload's staging is reused
+		return -1;
 	if (set_records(c, rec_off, n_rec))
 		return -1;
 	if (c->total_nt > 0 && seq == NULL)
@@ -1477,7 +1516,8 @@ extern "C" int gm_db_upload_chars_hostpack(gm_ctx *c, const char *seq, const int
 	if (join_uploader(c))
 		return -1;
 	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->copy_stream));
+	if (sync_uploads(c))
+		return -1;
 	if (set_records(c, rec_off, n_rec))
 		return -1;
 	const int64_t n = c->total_nt;
@@ -1540,7 +1580,8 @@ extern "C" int gm_db_set_device_chars(gm_ctx *c, const void *d_seq, const int64_
 	if (join_uploader(c))
 		return -1;
 	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->copy_stream));
+	if (sync_uploads(c))
+		return -1;
 	if (set_records(c, rec_off, n_rec))
 		return -1;
 	if (c->total_nt > 0 && d_seq == NULL)
@@ -1567,7 +1608,8 @@ extern "C" int gm_db_upload_fastn(gm_ctx *c, const char *text, size_t n_bytes)
 		return -1;
 	c->up_published = -1;
 	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->copy_stream));
+	if (sync_uploads(c))
+		return -1;
 	NvtxRange nvtx_("gpumotif: upload fastn (H2D + device reader)");
 	if (n_bytes > 0 && text[0] != '>')
 		return fail("fastn text does not begin with '>' (src/dbutil.c:56-60)");
@@ -1656,7 +1698,8 @@ extern "C" int gm_db_get_chars(gm_ctx *c, int64_t off, int64_t n, char *out)
 		return fail("range [%lld, %lld) outside the %lld uploaded nucleotides", (long long)off, (long long)(off + n),
 			    (long long)c->total_nt);
 	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->copy_stream));
+	if (sync_uploads(c))
+		return -1;
 	if (n > 0)
 		CU(cudaMemcpy(out, c->d_seq_chars + off, (size_t)n, cudaMemcpyDeviceToHost));
 	for (int64_t i = 0; i < n; i++) {
@@ -1789,6 +1832,10 @@ static int launch(gm_ctx *c)
 				CU(cudaStreamWaitEvent(c->stream, c->chunk_ev[ci], 0));
 				if (ci < n_chunks - 1)
 					A.g_end = std::min<int64_t>(A.g_end, c->chunk_end[ci] - slack);
+				// a chunk boundary that leaves only a sliver of the segment (segments and chunks
+				// both end on multiples of 16 Mnt) ends the segment there
+				if (seg_end - A.g_end <= 2 * slack)
+					seg_end = A.g_end;
 			}
 			A.n_tiles = (A.g_end - A.g_begin + c->par.tile - 1) / c->par.tile;
 			// the tile counter restarts for every filter launch
