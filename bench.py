@@ -338,8 +338,9 @@ class Bench:
 
         # ---- end-to-end leg: host characters in, candidates out, every step --------
         # Two ways over PCIe, both timed, the faster one reported (`e2e.upload`), the other kept
-        # in `e2e.other`: the characters as they are (1 B per nucleotide, packed on the device), or
-        # packed by a host thread team inside the timed region (gm_db_upload_chars_hostpack, 0.5 B).
+        # in `e2e.other_uploads`: the characters as they are (1 B per nucleotide, packed on the device), or
+        # gm_db_upload_chars_hostpack: a host thread team packs a share of every chunk inside the timed
+        # region (0.5 B per nucleotide) while the rest crosses as characters.
         def e2e_leg(host_pack):
             info = {}
 
@@ -363,7 +364,8 @@ class Bench:
         t_e2e, e2e_info, hits_e2e = legs[best]
         same_legs = all(len(v[2]) == len(hits_e2e) and v[2].tobytes() == hits_e2e.tobytes() for v in legs.values())
         res["upload"] = {"chars": "characters (1 B/nt), packed on the device",
-                         "hostpack": "4-bit codes packed by %d host threads inside the timed region (0.5 B/nt)"
+                         "hostpack": "a share of every chunk packed to 4-bit codes by %d host threads inside the timed "
+                                     "region, the rest sent as characters beside it (gm_db_upload_chars_hostpack)"
                          % self.pack_threads}[best]
         res["other_uploads"] = {m: {"ms_per_step": v[0] / steps, "h2d_bytes_per_step": int(v[1]["h2d"])}
                                 for m, v in legs.items() if m != best}

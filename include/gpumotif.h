@@ -108,7 +108,10 @@ int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec_off, int n
  * CPUs the process may run on, at most 16) turns the characters into the 4-bit codes
  * chunk by chunk in pinned staging owned by the context, and half a byte per
  * nucleotide crosses PCIe instead of one; `seq` may be pageable (the reference's
- * malloc'ed sbuf, src/rnamot.c:143-149) at no loss.  Returns at once: packing and copies
+ * malloc'ed sbuf, src/rnamot.c:143-149) at no loss.  When `seq` is pinned only a share of
+ * every chunk is packed on the host (GPUMOTIF_PACK_FRAC, default 0.045 per thread, at
+ * most 0.7) and the rest crosses as characters at the same time and is packed on the
+ * device: host cores and link work side by side.  Returns at once: packing and copies
  * run on while the caller goes on to gm_scan_launch / gm_scan, which search chunk i
  * while chunk i+1 is still being packed -- `seq` must stay valid and unchanged until
  * that call has returned.  The device never holds the characters, so gm_hit_windows

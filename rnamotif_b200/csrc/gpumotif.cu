@@ -1468,10 +1468,14 @@ extern "C" int gm_db_upload_chars(gm_ctx *c, const char *seq, const int64_t *rec
 	return 0;
 }
 
-// Host-packed upload: the thread team turns chunk i into 4-bit codes in a pinned ring slot,
-// the uploader thread copies it to its place in d_packed and publishes the chunk.  The
-// device never holds the characters (gm_hit_windows / gm_db_get_chars are refused).
-static void uploader_main(gm_ctx *c, const uint8_t *seq, int64_t chunk)
+// Host-packed upload: the thread team turns (a share of) chunk i into 4-bit codes in a pinned
+// ring slot, the uploader thread copies it to its place in d_packed and publishes the chunk.
+// When the caller's buffer is pinned the rest of the chunk goes over as characters at the same
+// time and is packed on the device: the host cores and the PCIe link then work side by side --
+// the packer alone is bound by host memory (~50 GB/s of input on the 16-core bench host), the
+// link alone by 49 GB/s of one-byte characters.  `frac` = the host-packed share of every chunk.
+// The device never holds all the characters (gm_hit_windows / gm_db_get_chars are refused).
+static void uploader_main(gm_ctx *c, const uint8_t *seq, int64_t chunk, double frac)
 {
 	auto bail = [&](const char *what, cudaError_t e) {
 		std::lock_guard<std::mutex> lk(c->up_m);
@@ -1485,17 +1489,40 @@ static void uploader_main(gm_ctx *c, const uint8_t *seq, int64_t chunk)
 	const int n_chunks = (int)c->chunk_end.size();
 	for (int i = 0; i < n_chunks; i++) {
 		const int64_t o = (int64_t)i * chunk, len = c->chunk_end[i] - o;
+		// [o, o + hp) is packed here, [o + hp, o + len) travels as characters
+		int64_t hp = frac >= 1.0 ? len : std::min<int64_t>(len, ((int64_t)(frac * (double)len) + 4095) & ~(int64_t)4095);
+		if (len - hp < 4096)
+			hp = len;
+		if (hp < len) {
+			// the character share first: the link works on it while the team packs
+			const int64_t oc = o + hp, lc = len - hp;
+			if ((e = cudaMemcpyAsync(c->d_chars + oc, seq + oc, (size_t)lc, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess ||
+			    (e = cudaEventRecord(c->cp_ev[i], c->copy_stream)) != cudaSuccess ||
+			    (e = cudaStreamWaitEvent(c->pack_stream, c->cp_ev[i], 0)) != cudaSuccess)
+				return bail("enqueue (characters)", e);
+			const int64_t groups = (lc + 15) / 16;
+			const int blocks = (int)std::min<int64_t>((groups + 255) / 256, (int64_t)c->n_sm * 16);
+			gm_pack_kernel<<<blocks, 256, 0, c->pack_stream>>>(c->d_chars + oc, c->d_packed + (oc >> 1), lc);
+			if ((e = cudaGetLastError()) != cudaSuccess)
+				return bail("pack kernel", e);
+		}
 		const int sl = i % GM_PACK_SLOTS;
 		if (i >= GM_PACK_SLOTS && (e = cudaEventSynchronize(c->slot_ev[sl])) != cudaSuccess)
 			return bail("cudaEventSynchronize", e);
 		uint8_t *dst = c->h_slot[sl];
-		c->team->run(seq + o, len, dst);
-		// whole 16-byte groups like the device's pack kernel writes them
-		const size_t nb = (size_t)((len + 1) >> 1), nb16 = (nb + 15) & ~(size_t)15;
-		memset(dst + nb, 0, nb16 - nb);
-		if ((e = cudaMemcpyAsync(c->d_packed + (o >> 1), dst, nb16, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess ||
+		c->team->run(seq + o, hp, dst);
+		size_t nb = (size_t)((hp + 1) >> 1);
+		if (hp == len) {
+			// whole 16-byte groups like the device's pack kernel writes them
+			const size_t nb16 = (nb + 15) & ~(size_t)15;
+			memset(dst + nb, 0, nb16 - nb);
+			nb = nb16;
+		}
+		// chunk_ev[i]: the packed share has arrived AND the character share is packed
+		if ((e = cudaMemcpyAsync(c->d_packed + (o >> 1), dst, nb, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess ||
 		    (e = cudaEventRecord(c->slot_ev[sl], c->copy_stream)) != cudaSuccess ||
-		    (e = cudaEventRecord(c->chunk_ev[i], c->copy_stream)) != cudaSuccess)
+		    (e = cudaStreamWaitEvent(c->pack_stream, c->slot_ev[sl], 0)) != cudaSuccess ||
+		    (e = cudaEventRecord(c->chunk_ev[i], c->pack_stream)) != cudaSuccess)
 			return bail("enqueue", e);
 		if (i == n_chunks - 1 && (e = cudaEventRecord(c->up_ev[1], c->copy_stream)) != cudaSuccess)
 			return bail("cudaEventRecord", e);
@@ -1550,6 +1577,27 @@ extern "C" int gm_db_upload_chars_hostpack(gm_ctx *c, const char *seq, const int
 			CU(cudaEventCreateWithFlags(&c->slot_ev[i], cudaEventDisableTiming));
 	if (c->team == NULL)
 		c->team = new PackTeam(host_pack_default_threads());
+	// share of every chunk packed on the host: all of it from pageable memory (a DMA from
+	// there would be staged synchronously); from pinned memory what the team keeps up with
+	// beside the link (GPUMOTIF_PACK_FRAC overrides; measured with 16 threads over 1 Gnt, ire: share
+	// 0.4 16.5 ms, 0.5 15.7, 0.6 15.1, 0.7 14.4 per step, 1.0 19.3; characters only 19.9)
+	double frac = 1.0;
+	{
+		cudaPointerAttributes at;
+		const bool pinned = n > 0 && cudaPointerGetAttributes(&at, seq) == cudaSuccess && at.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		if (pinned)
+			frac = std::min(0.7, 0.045 * c->team->size());
+		if (getenv("GPUMOTIF_PACK_FRAC") != NULL && (pinned || atof(getenv("GPUMOTIF_PACK_FRAC")) >= 1.0))
+			frac = std::max(0.05, std::min(1.0, atof(getenv("GPUMOTIF_PACK_FRAC"))));
+	}
+	if (frac < 1.0 && ensure((void **)&c->d_chars, &c->chars_cap, (size_t)n + 64))
+		return -1;
+	while (frac < 1.0 && (int)c->cp_ev.size() < n_chunks) {
+		cudaEvent_t e;
+		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		c->cp_ev.push_back(e);
+	}
 	while ((int)c->chunk_ev.size() < n_chunks) {
 		cudaEvent_t e;
 		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1565,9 +1613,20 @@ extern "C" int gm_db_upload_chars_hostpack(gm_ctx *c, const char *seq, const int
 	if (n_chunks == 0)
 		CU(cudaEventRecord(c->up_ev[1], c->copy_stream));
 	c->upload_fresh = true;
-	c->stats.h2d_bytes = (uint64_t)((n + 1) >> 1) + (uint64_t)(n_rec + 1) * 8;
+	{
+		// bytes over the link: half a byte per host-packed nucleotide, one per character sent as it is
+		uint64_t b = (uint64_t)(n_rec + 1) * 8;
+		for (int i = 0; i < n_chunks; i++) {
+			const int64_t o = (int64_t)i * chunk, len = c->chunk_end[i] - o;
+			int64_t hp = frac >= 1.0 ? len : std::min<int64_t>(len, ((int64_t)(frac * (double)len) + 4095) & ~(int64_t)4095);
+			if (len - hp < 4096)
+				hp = len;
+			b += (uint64_t)((hp + 1) >> 1) + (uint64_t)(len - hp);
+		}
+		c->stats.h2d_bytes = b;
+	}
 	if (n_chunks > 0)
-		c->up_thread = std::thread(uploader_main, c, (const uint8_t *)seq, chunk);
+		c->up_thread = std::thread(uploader_main, c, (const uint8_t *)seq, chunk, frac);
 	return 0;
 }
 

@@ -99,3 +99,33 @@ def test_hostpacked_upload_never_scanned_then_destroyed():
     ms.upload_hostpack(seq, off)
     ms.upload_hostpack(seq, off)
     ms.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frac", ["0.3", "0.6", "1.0"])
+def test_hostpacked_upload_from_pinned_memory_splits_chunks(frac, monkeypatch):
+    """From pinned memory a share of every chunk is packed on the host and the rest goes over as
+    characters (packed on the device) at the same time; the candidate stream does not depend on the share."""
+    import torch
+    monkeypatch.setenv("GPUMOTIF_CHUNK_NT", "16384")
+    monkeypatch.setenv("GPUMOTIF_PACK_THREADS", "4")
+    monkeypatch.setenv("GPUMOTIF_PACK_FRAC", frac)
+    plan = helpers.load_plan("trna")
+    rng = np.random.default_rng(12)
+    lengths = list(rng.integers(0, 6000, size=30)) + [150001, 7, 90000]
+    ids, seq, off = synth.random_records(29, lengths, planted=True, iupac_rate=0.002)
+    ref, _ = oracle_port.scan_db(plan, seq, off, True)
+    pinned = torch.empty(len(seq), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = seq
+    ms = gpumotif.MotifSearch(plan)
+    for _ in range(2):
+        ms.upload_ptr(pinned.data_ptr(), off, host_pack=True)
+        hits = ms.scan()
+        helpers.assert_same_hits(hits, ref, f"pinned host-packed upload, share {frac}")
+    st = ms.stats()
+    ms.close()
+    n = int(off[-1])
+    if frac == "1.0":
+        assert st.h2d_bytes < 0.55 * n + 8 * len(off) + 64
+    else:
+        assert 0.5 * n < st.h2d_bytes < n
