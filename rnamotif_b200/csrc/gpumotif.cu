@@ -1752,7 +1752,8 @@ extern "C" int gm_db_get_chars(gm_ctx *c, int64_t off, int64_t n, char *out)
 	if (c == NULL || out == NULL || off < 0 || n < 0)
 		return fail("bad argument");
 	if (c->d_seq_chars == NULL)
-		return fail("no database uploaded");
+		return fail(c->up_published >= 0 ? "the device holds no characters after gm_db_upload_chars_hostpack (the caller has them)"
+					   : "no database uploaded");
 	if (off + n > c->total_nt)
 		return fail("range [%lld, %lld) outside the %lld uploaded nucleotides", (long long)off, (long long)(off + n),
 			    (long long)c->total_nt);
@@ -2207,7 +2208,8 @@ extern "C" int gm_hit_windows(gm_ctx *c, int lead, int trail, const char **win, 
 	if (c->pending)
 		return fail("a scan is in flight");
 	if (c->d_seq_chars == NULL)
-		return fail("no database uploaded");
+		return fail(c->up_published >= 0 ? "the device holds no characters after gm_db_upload_chars_hostpack (the caller has them)"
+					   : "no database uploaded");
 	CU(cudaSetDevice(c->device));
 	NvtxRange nvtx_("gpumotif: hit windows");
 	const int wlen = (lead + c->par.w_winsize + trail + 1 + 7) & ~7;
