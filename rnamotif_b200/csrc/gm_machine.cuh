@@ -1367,9 +1367,62 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 				const int64_t roff = A.rec_off[L.rec];
 				const int slen = L.slen, comp = L.comp, c00 = L.szero - Lc;
 				uint32_t *mb = const_cast<uint32_t *>(mypb.base);
+				// Lite plans: eight window positions at a time (expand8, gm_tilebits.h) -- two aligned
+				// words of the packed database and a funnel shift bring their codes in line; on the
+				// complementary strand the same forward word gives the complement bytes in reversed
+				// order and the bit-reversed bitset bytes; positions outside the record read as code 0
+				// (0x40 on both strands).  Checked against the per-nucleotide loop below on the host
+				// (tests/csrc/winbuild_check.cpp).  The full machine keeps the per-nucleotide loop: with
+				// this build in it the kernel (96 instead of 124 registers) never finished on
+				// pseudoknot plans, for a reason not found (profiles/win_probe.sh).
+				const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.packed);
+				const int64_t wmax = (A.total_nt >> 3) + 1; // last word that may be read (the buffer has slack)
+				uint32_t *win32 = reinterpret_cast<uint32_t *>(mywin);
 				for (int w = 0; w < nwl; w++) {
 					uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
 					const int i0 = w << 5;
+					if (!FULL) {
+#pragma unroll
+					for (int g = 0; g < 4; g++) {
+						const int t0 = i0 + 8 * g;
+						if (t0 < Wtot) {
+							const int c0 = c00 + t0;
+							const int jlo = max(0, -c0), jhi = min(min(8, slen - c0), Wtot - t0);
+							uint32_t x = 0;
+							if (jhi > jlo) {
+								const int64_t f0 = comp ? roff + (slen - 1 - (c0 + 7)) : roff + c0;
+								const int64_t wi = f0 >> 3;
+								const int sh = (int)(f0 & 7) * 4;
+								x = __funnelshift_r(pw[max((int64_t)0, min(wi, wmax))], pw[max((int64_t)0, min(wi + 1, wmax))], sh);
+								if (jlo > 0 || jhi < 8) {
+									const int nlo = comp ? 8 - jhi : jlo, nhi = comp ? 8 - jlo : jhi;
+									x &= (nhi >= 8 ? ~0u : ((1u << (4 * nhi)) - 1u)) & (~0u << (4 * nlo));
+								}
+							}
+							uint32_t f0_, f1_, r0_, r1_, bits;
+							expand8(x, f0_, f1_, r0_, r1_, bits);
+							if (comp) {
+								f0_ = r0_;
+								f1_ = r1_;
+								bits = __brev(bits);
+								if (jlo > 0 || jhi < 8) {
+									for (int jj = 0; jj < 8; jj++)
+										if (jj < jlo || jj >= jhi) {
+											uint32_t &wd = jj < 4 ? f0_ : f1_;
+											wd = (wd & ~(0xffu << (8 * (jj & 3)))) | (0x40u << (8 * (jj & 3)));
+										}
+								}
+							}
+							win32[t0 >> 2] = f0_;
+							if (t0 + 4 < Wtot)
+								win32[(t0 >> 2) + 1] = f1_;
+							b0 |= (bits & 0xffu) << (8 * g);
+							b1 |= ((bits >> 8) & 0xffu) << (8 * g);
+							b2 |= ((bits >> 16) & 0xffu) << (8 * g);
+							b3 |= (bits >> 24) << (8 * g);
+						}
+					}
+					} else {
 					for (int t = 0; t < 32 && i0 + t < Wtot; t++) {
 						const int c = c00 + i0 + t; // strand coordinate
 						uint8_t v = (uint8_t)(4 << 4);
@@ -1386,6 +1439,7 @@ __global__ void gm_dfs_kernel(const ScanArgs A)
 						b1 |= (uint32_t)(bc == 1) << t;
 						b2 |= (uint32_t)(bc == 2) << t;
 						b3 |= (uint32_t)(bc == 3) << t;
+					}
 					}
 					mb[0 * nwl + w] = b0;
 					mb[1 * nwl + w] = b1;

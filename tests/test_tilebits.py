@@ -14,3 +14,11 @@ def test_expand8_matches_per_nucleotide_definitions(tmp_path):
                     os.path.join(helpers.HERE, "csrc", "tilebits_check.cpp"), "-o", exe], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.strip() == "ok", out
+
+
+def test_lane_window_build_matches_per_nucleotide_loop(tmp_path):
+    exe = str(tmp_path / "winbuild_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(helpers.ROOT, "rnamotif_b200", "csrc"),
+                    os.path.join(helpers.HERE, "csrc", "winbuild_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "ok", out
