@@ -696,6 +696,7 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 	// Composition chain.  Projection of every pair table onto its strands: a base
 	// that pairs with nothing at a strand can only sit there as a mispair.
 	par->chain = 0;
+	double chain_est = 1.0;
 	if (getenv("GPUMOTIF_NO_CHAIN") == NULL && getenv("GPUMOTIF_NO_SIEVE") == NULL) {
 		struct Step { int mn, mx, cm, both, con; unsigned bud; };
 		std::vector<Step> steps;
@@ -797,7 +798,51 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 			}
 			if (!par->sieve)
 				par->sieve = 1; // the chain alone makes a sieve
+			// share of the starts the chain lets through, for the two-stage decision below: every
+			// constrained strand at its shortest, independent uniform bases, dilated by the ranges of
+			// the unconstrained stretches between them
+			double est = 1.0;
+			for (const Step &st : steps) {
+				if (!st.con) {
+					est *= (double)(st.mx - st.mn + 1);
+					continue;
+				}
+				int nb = 0;
+				for (int x = 0; x < 4; x++)
+					nb += (st.cm >> x) & 1;
+				const double q = nb / 4.0;
+				const int b0 = (int)(st.bud & 3u), L0 = st.mn;
+				double pr = 0, c = 1;
+				for (int k = 0; k <= std::min(b0, L0); k++) {
+					pr += c * pow(q, L0 - k) * pow(1 - q, k);
+					c = c * (L0 - k) / (k + 1);
+				}
+				est *= std::min(1.0, pr) * (st.mx - st.mn + 1);
+			}
+			chain_est = std::min(1.0, est);
 		}
+	}
+	// Two-stage sieve without look-ahead bitsets: when the literal or the chain alone leaves few starts
+	// (estimated for independent uniform bases), stage 1 is just those words and the first helix's
+	// span-end mask is taken per surviving start (accept2) -- its word-parallel pass over every span
+	// offset is the larger part of the filter kernel for such plans (pk1: 20 steps for a term that
+	// 84 % of the starts pass, beside a literal that 5 % pass).
+	if (par->sieve && par->sv_helix && par->pf_search >= 0 && !par->pf_deep && !par->sv_two &&
+	    getenv("GPUMOTIF_NO_TWO_STAGE") == NULL) {
+		double est = 1.0;
+		if (par->lit_present) {
+			const int L0 = par->lit_len, mm = par->lit_mm;
+			double pr = 0, c = 1;
+			for (int k = 0; k <= std::min(mm, L0); k++) {
+				pr += c * pow(0.25, L0 - k) * pow(0.75, k);
+				c = c * (L0 - k) / (k + 1);
+			}
+			est = std::min(1.0, pr * (par->lit_lmax - par->lit_lmin + 1));
+		}
+		if (par->chain)
+			est *= chain_est;
+		if (est < 0.08 || getenv("GPUMOTIF_TWO_STAGE") != NULL)
+			par->sv_two = 1;
 	}
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
