@@ -843,6 +843,9 @@ static int check_plan(const gm_plan_t *pl, DevSearch *ds, DevParams *par)
 			est *= chain_est;
 		if (est < 0.08 || getenv("GPUMOTIF_TWO_STAGE") != NULL)
 			par->sv_two = 1;
+		if (getenv("GPUMOTIF_DEBUG") != NULL)
+			fprintf(stderr, "gpumotif: stage-1 share estimate %.4f (literal %d, chain %d steps, chain share %.4f)\n", est,
+				par->lit_present, par->chain, chain_est);
 	}
 	par->lite = 1;
 	for (int s = 0; s < NS; s++)
