@@ -71,10 +71,10 @@ def test_public_headers_are_plain_c():
 
 def test_level0_organisation_chosen_per_plan():
     """gm_plan_describe (host side): the two-stage sieve for plans whose look-ahead bitsets (trna), literal (ire,
-    pk1) or chain (descr.quad) alone leave few starts; the single-stage sieve where the first helix itself is
+    pk1) or chain (descr.quad, qu+tr) alone leave few starts; the single-stage sieve where the first helix itself is
     the filter (score.1)."""
     def level0(name):
         return gpumotif.plan_describe(helpers.load_plan(name)).splitlines()[1]
-    for name in ("trna", "ire", "pk1", "descr.quad"):
+    for name in ("trna", "ire", "pk1", "descr.quad", "qu+tr"):
         assert "sieve 1 two-stage 1" in level0(name), (name, level0(name))
     assert "sieve 1 two-stage 0" in level0("score.1"), level0("score.1")
